@@ -1,0 +1,655 @@
+"""Fixed-width packed state layout.
+
+A state is ``W`` 64-bit words.  Every state variable gets a *layout type* (inferred from the
+spec's own type invariant, e.g. KafkaReplication.tla:101-107, see ``typeinfer.py``); the leaves
+of the type tree are *atoms*: unsigned bit-fields that never straddle a word.
+
+Type            encoding
+--------------  -----------------------------------------------------------------------------
+TInt(lo, hi)    code = value - lo
+TEnum(atoms)    code = index of the model value / string in the (gid-sorted) universe
+TUnion(alts)    code = offset(alt) + alt code          (records[o] is a record or Nil, FiniteReplicatedLog.tla:41-44)
+TRec / TFn      product of the members: separate atoms at top level, mixed radix when nested in a set/union
+TSet bitmap     one bit per possible element (element code = bit index)
+TSet array      count + ``cap`` element codes kept sorted ascending, unused slots 0 -> canonical, so
+                equal sets pack to equal bits (leaderAndIsrRequests, KafkaReplication.tla:66)
+
+Every type offers the same operations in two worlds: ``py_*`` on Python values (Init states,
+decoding traces, tests) and ``read``/``write``/``enc``/``dec`` on symbolic values, emitting C.
+"""
+from __future__ import annotations
+
+from ..frontend.cfg import ModelValue
+from ..frontend.values import FnVal, fmt, sort_key
+from .svals import (LowerError, SAtom, SBool, SFn, SInt, SRec, SSet, SUnion, is_atom_const,
+                    is_const, is_int_const, kind_sig)
+
+
+def bits_for(card: int) -> int:
+    return max(0, (card - 1).bit_length())
+
+
+class Atom:
+    __slots__ = ("index", "path", "bits", "word", "shift")
+
+    def __init__(self, index, path, bits):
+        self.index, self.path, self.bits = index, path, bits
+        self.word = self.shift = 0
+
+    @property
+    def mask(self) -> int:
+        return (1 << self.bits) - 1
+
+
+class Layout:
+    def __init__(self):
+        self.atoms: list[Atom] = []
+        self.var_types: dict[str, "Ty"] = {}
+        self.variables: list[str] = []
+        self.words = 0
+        self.bits = 0
+
+    def new_atom(self, path: str, bits: int) -> Atom:
+        if bits > 32:
+            raise LowerError(f"atom {path} needs {bits} bits (> 32)")
+        a = Atom(len(self.atoms), path, bits)
+        self.atoms.append(a)
+        return a
+
+    def finish(self):
+        word, used = 0, 0
+        for a in self.atoms:
+            if used + a.bits > 64:
+                word, used = word + 1, 0
+            a.word, a.shift = word, used
+            used += a.bits
+            self.bits += a.bits
+        self.words = word + 1
+
+    # -- python-side packing -------------------------------------------------
+    def py_pack(self, state: dict) -> list[int]:
+        codes: dict[int, int] = {}
+        for v in self.variables:
+            self.var_types[v].py_write(state[v], codes)
+        words = [0] * self.words
+        for a in self.atoms:
+            c = codes.get(a.index, 0)
+            if c < 0 or c > a.mask:
+                raise LowerError(f"value for {a.path} does not fit its layout ({c} in {a.bits} bits)")
+            words[a.word] |= c << a.shift
+        return words
+
+    def py_unpack(self, words) -> dict:
+        codes = {a.index: (int(words[a.word]) >> a.shift) & a.mask for a in self.atoms}
+        return {v: self.var_types[v].py_read(codes) for v in self.variables}
+
+    def describe(self) -> dict:
+        return {
+            "words": self.words, "bits": self.bits, "variables": self.variables,
+            "atoms": [{"path": a.path, "bits": a.bits, "word": a.word, "shift": a.shift} for a in self.atoms],
+            "types": {v: self.var_types[v].describe() for v in self.variables},
+        }
+
+
+# ---------------------------------------------------------------------------
+class Ty:
+    card: int = 0          # number of values if the type is codeable as one integer, else 0
+
+    def alloc(self, lay: Layout, path: str):
+        raise NotImplementedError
+
+    def describe(self):
+        raise NotImplementedError
+
+    def kind(self) -> str:
+        raise NotImplementedError
+
+    # python values
+    def py_enc(self, v) -> int:
+        raise LowerError(f"type {self.describe()} is not scalar-codeable")
+
+    def py_dec(self, code: int):
+        raise LowerError(f"type {self.describe()} is not scalar-codeable")
+
+    def py_write(self, v, codes: dict):
+        codes[self.atom.index] = self.py_enc(v)
+
+    def py_read(self, codes: dict):
+        return self.py_dec(codes[self.atom.index]) if self.atom is not None else self.py_dec(0)
+
+    # symbolic values; ``lw`` is the Lowerer
+    def enc(self, lw, v) -> str:
+        raise LowerError(f"type {self.describe()} is not scalar-codeable")
+
+    def dec(self, lw, code: str):
+        raise LowerError(f"type {self.describe()} is not scalar-codeable")
+
+    def read(self, lw):
+        if self.atom is None:
+            return self.py_dec(0)
+        return self.dec(lw, f"a{self.atom.index}")
+
+    def write(self, lw, v, out: dict):
+        if self.atom is None:
+            return
+        out[self.atom.index] = self.enc(lw, v)
+
+    def _alloc_scalar(self, lay: Layout, path: str):
+        b = bits_for(self.card)
+        self.atom = lay.new_atom(path, b) if b > 0 else None
+
+
+class TInt(Ty):
+    def __init__(self, lo: int, hi: int):
+        self.lo, self.hi = lo, hi
+        self.card = hi - lo + 1
+        self.atom = None
+
+    def kind(self):
+        return "int"
+
+    def describe(self):
+        return {"t": "int", "lo": self.lo, "hi": self.hi}
+
+    def alloc(self, lay, path):
+        self._alloc_scalar(lay, path)
+
+    def py_enc(self, v):
+        if not is_int_const(v) or not (self.lo <= v <= self.hi):
+            raise LowerError(f"value {fmt(v)} outside layout range {self.lo}..{self.hi}")
+        return v - self.lo
+
+    def py_dec(self, code):
+        return code + self.lo
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            return lw.enc_union_into(self, v)
+        if not isinstance(v, SInt):
+            raise LowerError(f"cannot store {v!r} in an integer field")
+        if v.lo < self.lo or v.hi > self.hi:
+            lw.trap_unless(lw.b_and([lw.cmp(">=", v, self.lo), lw.cmp("<=", v, self.hi)]))
+        return lw.tmp_int(f"({v.s} - {self.lo})" if self.lo else v.s)
+
+    def dec(self, lw, code):
+        if self.card == 1:
+            return self.lo
+        return SInt(f"((int){code} + {self.lo})" if self.lo else f"(int){code}", self.lo, self.hi)
+
+
+class TEnum(Ty):
+    def __init__(self, atoms: list, gids: dict):
+        self.atoms = sorted(atoms, key=lambda a: gids[a])
+        self.gid = {a: gids[a] for a in self.atoms}
+        self.card = len(self.atoms)
+        g = [self.gid[a] for a in self.atoms]
+        self.base = g[0]
+        self.contiguous = g == list(range(g[0], g[0] + len(g)))
+        self.atom = None
+
+    def kind(self):
+        return "atom"
+
+    def describe(self):
+        return {"t": "enum", "values": [fmt(a) for a in self.atoms]}
+
+    def alloc(self, lay, path):
+        self._alloc_scalar(lay, path)
+
+    def py_enc(self, v):
+        if v not in self.gid:
+            raise LowerError(f"value {fmt(v)} outside layout enum {[fmt(a) for a in self.atoms]}")
+        return self.atoms.index(v)
+
+    def py_dec(self, code):
+        return self.atoms[code]
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            return lw.enc_union_into(self, v)
+        if not isinstance(v, SAtom):
+            raise LowerError(f"cannot store {v!r} in an enum field")
+        if not set(v.uni) <= set(self.atoms):
+            lw.trap_unless(lw.b_or([SBool(f"({v.s} == {self.gid[a]})") for a in self.atoms]))
+        if self.contiguous:
+            return lw.tmp_int(f"({v.s} - {self.base})" if self.base else v.s)
+        e = "0"
+        for i, a in reversed(list(enumerate(self.atoms))):
+            e = f"({v.s} == {self.gid[a]} ? {i} : {e})"
+        return lw.tmp_int(e)
+
+    def dec(self, lw, code):
+        if self.card == 1:
+            return self.atoms[0]
+        if self.contiguous:
+            return SAtom(f"((int){code} + {self.base})" if self.base else f"(int){code}", tuple(self.atoms))
+        e = str(self.gid[self.atoms[-1]])
+        for i, a in reversed(list(enumerate(self.atoms[:-1]))):
+            e = f"({code} == {i} ? {self.gid[a]} : {e})"
+        return SAtom(lw.tmp_int(e), tuple(self.atoms))
+
+
+class TRec(Ty):
+    def __init__(self, fields: dict):
+        self.fields = dict(fields)          # name -> Ty, in declaration order
+        self.card = 1
+        for t in self.fields.values():
+            self.card = self.card * t.card if (t.card and self.card) else 0
+        if self.card > (1 << 30):
+            self.card = 0
+        self.atom = None
+
+    def kind(self):
+        return "rec:" + ",".join(sorted(self.fields))
+
+    def describe(self):
+        return {"t": "rec", "fields": {f: t.describe() for f, t in self.fields.items()}}
+
+    def alloc(self, lay, path):
+        for f, t in self.fields.items():
+            t.alloc(lay, f"{path}.{f}")
+
+    def _get(self, v, f):
+        if isinstance(v, FnVal):
+            return v.apply(f)
+        return v.fields[f]
+
+    def _check(self, v):
+        names = set(v.domain()) if isinstance(v, FnVal) else set(v.fields) if isinstance(v, SRec) else None
+        if names != set(self.fields):
+            raise LowerError(f"cannot store {v!r} in record layout {list(self.fields)}")
+
+    def py_enc(self, v):
+        if not isinstance(v, FnVal) or set(v.domain()) != set(self.fields):
+            raise LowerError(f"value {fmt(v)} is not a record with fields {list(self.fields)}")
+        code, stride = 0, 1
+        for f, t in self.fields.items():
+            code += t.py_enc(v.apply(f)) * stride
+            stride *= t.card
+        return code
+
+    def py_dec(self, code):
+        d = {}
+        for f, t in self.fields.items():
+            d[f] = t.py_dec(code % t.card)
+            code //= t.card
+        return FnVal(d)
+
+    def py_write(self, v, codes):
+        if not isinstance(v, FnVal) or set(v.domain()) != set(self.fields):
+            raise LowerError(f"value {fmt(v)} is not a record with fields {list(self.fields)}")
+        for f, t in self.fields.items():
+            t.py_write(v.apply(f), codes)
+
+    def py_read(self, codes):
+        return FnVal({f: t.py_read(codes) for f, t in self.fields.items()})
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            return lw.enc_union_into(self, v)
+        self._check(v)
+        terms, stride = [], 1
+        for f, t in self.fields.items():
+            c = t.enc(lw, self._get(v, f))
+            terms.append(c if stride == 1 else f"{c} * {stride}")
+            stride *= t.card
+        return lw.tmp_int("(" + " + ".join(terms) + ")")
+
+    def dec(self, lw, code):
+        out, stride = {}, 1
+        for f, t in self.fields.items():
+            if t.card == 1:
+                out[f] = t.py_dec(0)
+            else:
+                x = code if stride == 1 else f"({code} / {stride})"
+                if stride * t.card < self.card:
+                    x = f"({x} % {t.card})"
+                out[f] = t.dec(lw, lw.tmp_int(x))
+            stride *= t.card
+        return SRec(out)
+
+    def read(self, lw):
+        return SRec({f: lw.read_ty(t) for f, t in self.fields.items()})
+
+    def write(self, lw, v, out):
+        if isinstance(v, SUnion):
+            v = lw.narrow_union(v, self.kind())
+        self._check(v)
+        for f, t in self.fields.items():
+            x = self._get(v, f)
+            if x is lw.read_cache.get(id(t)):
+                continue                      # member untouched since it was read
+            t.write(lw, x, out)
+
+
+class TFn(Ty):
+    def __init__(self, keys: list, elem_types: list):
+        self.keys = list(keys)
+        self.elems = list(elem_types)       # one Ty instance per key (separate atoms)
+        self.card = 1
+        for t in self.elems:
+            self.card = self.card * t.card if (t.card and self.card) else 0
+        if self.card > (1 << 30):
+            self.card = 0
+        self.atom = None
+
+    def kind(self):
+        return "fn"
+
+    def describe(self):
+        return {"t": "fn", "keys": [fmt(k) for k in self.keys], "elem": self.elems[0].describe()}
+
+    def alloc(self, lay, path):
+        for k, t in zip(self.keys, self.elems):
+            t.alloc(lay, f"{path}[{fmt(k)}]")
+
+    def _vals(self, v):
+        if isinstance(v, FnVal):
+            if set(v.domain()) != set(self.keys):
+                raise LowerError(f"function domain mismatch storing {fmt(v)}")
+            return [v.apply(k) for k in self.keys]
+        if isinstance(v, SFn):
+            if set(v.keys) != set(self.keys):
+                raise LowerError("function domain mismatch")
+            m = dict(zip(v.keys, v.vals))
+            return [m[k] for k in self.keys]
+        raise LowerError(f"cannot store {v!r} in a function layout")
+
+    def py_enc(self, v):
+        code, stride = 0, 1
+        for t, x in zip(self.elems, self._vals(v)):
+            code += t.py_enc(x) * stride
+            stride *= t.card
+        return code
+
+    def py_dec(self, code):
+        d = {}
+        for k, t in zip(self.keys, self.elems):
+            d[k] = t.py_dec(code % t.card)
+            code //= t.card
+        return FnVal(d)
+
+    def py_write(self, v, codes):
+        for t, x in zip(self.elems, self._vals(v)):
+            t.py_write(x, codes)
+
+    def py_read(self, codes):
+        return FnVal({k: t.py_read(codes) for k, t in zip(self.keys, self.elems)})
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        terms, stride = [], 1
+        for t, x in zip(self.elems, self._vals(v)):
+            c = t.enc(lw, x)
+            terms.append(c if stride == 1 else f"{c} * {stride}")
+            stride *= t.card
+        return lw.tmp_int("(" + " + ".join(terms) + ")")
+
+    def dec(self, lw, code):
+        vals, stride = [], 1
+        for t in self.elems:
+            x = code if stride == 1 else f"({code} / {stride})"
+            if stride * t.card < self.card:
+                x = f"({x} % {t.card})"
+            vals.append(t.dec(lw, lw.tmp_int(x)) if t.card > 1 else t.py_dec(0))
+            stride *= t.card
+        return SFn(self.keys, vals)
+
+    def read(self, lw):
+        return SFn(self.keys, [lw.read_ty(t) for t in self.elems])
+
+    def write(self, lw, v, out):
+        for t, x in zip(self.elems, self._vals(v)):
+            if x is lw.read_cache.get(id(t)):
+                continue
+            t.write(lw, x, out)
+
+
+class TUnion(Ty):
+    def __init__(self, alts: list):
+        self.alts = list(alts)
+        if any(not t.card for t in alts):
+            raise LowerError("union alternatives must be scalar-codeable")
+        kinds = [t.kind() for t in alts]
+        if len(set(kinds)) != len(kinds):
+            raise LowerError(f"union alternatives must have distinct kinds, got {kinds}")
+        self.offsets, off = [], 0
+        for t in alts:
+            self.offsets.append(off)
+            off += t.card
+        self.card = off
+        self.atom = None
+
+    def kind(self):
+        return "union"
+
+    def describe(self):
+        return {"t": "union", "alts": [t.describe() for t in self.alts]}
+
+    def alloc(self, lay, path):
+        self._alloc_scalar(lay, path)
+
+    def _alt_for_kind(self, k: str):
+        for i, t in enumerate(self.alts):
+            if t.kind() == k:
+                return i
+        return None
+
+    def py_enc(self, v):
+        i = self._alt_for_kind(kind_sig(v))
+        if i is None:
+            raise LowerError(f"value {fmt(v)} fits no alternative of {self.describe()}")
+        return self.offsets[i] + self.alts[i].py_enc(v)
+
+    def py_dec(self, code):
+        for t, off in zip(reversed(self.alts), reversed(self.offsets)):
+            if code >= off:
+                return t.py_dec(code - off)
+        raise LowerError("bad union code")
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            e = None
+            for g, x in reversed(v.alts):
+                c = self.enc(lw, x)
+                e = c if e is None else f"({lw.bstr(g)} ? {c} : {e})"
+            return lw.tmp_int(e if e is not None else "0")
+        i = self._alt_for_kind(kind_sig(v))
+        if i is None:
+            raise LowerError(f"value {v!r} fits no alternative of {self.describe()}")
+        c = self.alts[i].enc(lw, v)
+        return lw.tmp_int(f"({c} + {self.offsets[i]})" if self.offsets[i] else c)
+
+    def dec(self, lw, code):
+        alts = []
+        n = len(self.alts)
+        for i, (t, off) in enumerate(zip(self.alts, self.offsets)):
+            conds = []
+            if i > 0:
+                conds.append(f"{code} >= {off}")
+            if i < n - 1:
+                conds.append(f"{code} < {off + t.card}")
+            g = SBool(lw.tmp_bool("(" + " && ".join(conds) + ")")) if conds else True
+            if t.card == 1:
+                val = t.py_dec(0)
+            else:
+                val = t.dec(lw, lw.tmp_int(f"({code} - {off})") if off else code)
+            alts.append((g, val))
+        return SUnion(alts)
+
+
+class TSet(Ty):
+    """Set of ``elem``; bitmap over element codes, or sorted bounded array when ``cap`` is given."""
+
+    def __init__(self, elem: Ty, cap: int | None = None):
+        if not elem.card:
+            raise LowerError("set element type must be scalar-codeable")
+        self.elem, self.cap = elem, cap
+        self.card = (1 << elem.card) if (cap is None and elem.card <= 30) else 0
+        self.chunks: list[Atom] = []
+        self.count_atom = None
+        self.slots: list[Atom] = []
+        self.atom = None
+
+    def kind(self):
+        return "set"
+
+    def describe(self):
+        d = {"t": "set", "elem": self.elem.describe(), "repr": "bitmap" if self.cap is None else "array"}
+        if self.cap is not None:
+            d["cap"] = self.cap
+        return d
+
+    def alloc(self, lay, path):
+        if self.cap is None:
+            n, i = self.elem.card, 0
+            while n > 0:
+                b = min(32, n)
+                self.chunks.append(lay.new_atom(f"{path}#bits{i}", b))
+                n -= b
+                i += 1
+        else:
+            self.count_atom = lay.new_atom(f"{path}#count", bits_for(self.cap + 1))
+            eb = bits_for(self.elem.card)
+            self.slots = [lay.new_atom(f"{path}#slot{i}", eb) for i in range(self.cap)]
+
+    # python
+    def _py_codes(self, v) -> list[int]:
+        if not isinstance(v, frozenset):
+            raise LowerError(f"value {fmt(v)} is not a set")
+        return sorted(self.elem.py_enc(x) for x in v)
+
+    def py_enc(self, v):
+        if not self.card:
+            return super().py_enc(v)
+        m = 0
+        for c in self._py_codes(v):
+            m |= 1 << c
+        return m
+
+    def py_dec(self, code):
+        if not self.card:
+            return super().py_dec(code)
+        return frozenset(self.elem.py_dec(j) for j in range(self.elem.card) if (code >> j) & 1)
+
+    def py_write(self, v, codes):
+        cs = self._py_codes(v)
+        if self.cap is None:
+            for i, a in enumerate(self.chunks):
+                codes[a.index] = sum(1 << (c - 32 * i) for c in cs if 32 * i <= c < 32 * i + a.bits)
+        else:
+            if len(cs) > self.cap:
+                raise LowerError(f"set {fmt(v)} exceeds layout capacity {self.cap}")
+            codes[self.count_atom.index] = len(cs)
+            for a, c in zip(self.slots, cs):
+                codes[a.index] = c
+
+    def py_read(self, codes):
+        if self.cap is None:
+            out = []
+            for i, a in enumerate(self.chunks):
+                m = codes[a.index]
+                out += [self.elem.py_dec(32 * i + j) for j in range(a.bits) if (m >> j) & 1]
+            return frozenset(out)
+        n = codes[self.count_atom.index]
+        return frozenset(self.elem.py_dec(codes[a.index]) for a in self.slots[:n])
+
+    # symbolic
+    def enc(self, lw, v):
+        if not self.card:
+            return super().enc(lw, v)
+        if is_const(v):
+            return str(self.py_enc(v))
+        return self._bitmap_exprs(lw, v, 1)[0]
+
+    def dec(self, lw, code):
+        if not self.card:
+            return super().dec(lw, code)
+        return SSet([(SBool(f"(({code} >> {j}) & 1u)"), self.elem.py_dec(j)) for j in range(self.elem.card)])
+
+    def _items(self, lw, v):
+        if isinstance(v, frozenset):
+            return [(True, x) for x in sorted(v, key=sort_key)]
+        if isinstance(v, SSet):
+            return v.items
+        raise LowerError(f"cannot store {v!r} in a set field")
+
+    def _bitmap_exprs(self, lw, v, nchunks: int) -> list[str]:
+        terms: list[list[str]] = [[] for _ in range(nchunks)]
+        for g, x in self._items(lw, v):
+            if is_const(x):
+                try:
+                    j = self.elem.py_enc(x)
+                except LowerError:
+                    lw.trap_unless(lw.b_not(g))
+                    continue
+                bit = f"{1 << (j % 32)}u"
+                terms[j // 32].append(bit if g is True else f"({g.s} ? {bit} : 0u)")
+            else:
+                c = self.elem.enc(lw, x)
+                gs = lw.bstr(g)
+                if nchunks == 1:
+                    terms[0].append(f"({gs} ? (1u << {c}) : 0u)")
+                else:
+                    for k in range(nchunks):
+                        terms[k].append(f"(({gs} && ({c} >> 5) == {k}) ? (1u << ({c} & 31)) : 0u)")
+        return [lw.tmp_uint("(" + " | ".join(t) + ")") if t else "0u" for t in terms]
+
+    def read(self, lw):
+        if self.cap is None:
+            items = []
+            for i, a in enumerate(self.chunks):
+                for j in range(a.bits):
+                    items.append((SBool(f"((a{a.index} >> {j}) & 1u)"), self.elem.py_dec(32 * i + j)))
+            return SSet(items)
+        items = []
+        for i, a in enumerate(self.slots):
+            g = SBool(f"({i} < (int)a{self.count_atom.index})")
+            items.append((g, self.elem.dec(lw, f"a{a.index}")))
+        return SSet(items)
+
+    def write(self, lw, v, out):
+        if self.cap is None:
+            if is_const(v):
+                codes: dict = {}
+                self.py_write(v, codes)
+                for a in self.chunks:
+                    out[a.index] = f"{codes[a.index]}u"
+                return
+            for a, e in zip(self.chunks, self._bitmap_exprs(lw, v, len(self.chunks))):
+                out[a.index] = e
+            return
+        if is_const(v):
+            codes = {}
+            self.py_write(v, codes)
+            out[self.count_atom.index] = str(codes[self.count_atom.index])
+            for a in self.slots:
+                out[a.index] = str(codes.get(a.index, 0))
+            return
+        # canonical sorted array: dedup, rank, scatter  (O(m^2) compares, m = #candidate elements)
+        items = self._items(lw, v)
+        cs = [lw.tmp_int(self.elem.enc(lw, x)) for _, x in items]
+        ps: list[str] = []
+        for i, (g, _) in enumerate(items):
+            terms = [lw.bstr(g)] + [f"!({ps[j]} && {cs[j]} == {cs[i]})" for j in range(i)]
+            ps.append(lw.tmp_bool("(" + " && ".join(terms) + ")"))
+        ranks = []
+        for i in range(len(items)):
+            terms = [f"(int)({ps[j]} && {cs[j]} < {cs[i]})" for j in range(len(items)) if j != i]
+            ranks.append(lw.tmp_int("(" + " + ".join(terms) + ")") if terms else "0")
+        count = lw.tmp_int("(" + " + ".join(f"(int){p}" for p in ps) + ")") if ps else "0"
+        if len(items) > self.cap:
+            lw.trap_unless(SBool(f"({count} <= {self.cap})"))
+        out[self.count_atom.index] = count
+        for r, a in enumerate(self.slots):
+            terms = [f"(({ps[i]} && {ranks[i]} == {r}) ? {cs[i]} : 0)" for i in range(len(items))]
+            out[a.index] = lw.tmp_int("(" + " | ".join(terms) + ")") if terms else "0"

@@ -1,0 +1,462 @@
+"""Lowering driver: ``Module.tla`` + ``Module.cfg``  ->  ``LoweredModel`` (C++ header + layout).
+
+The header is the "CUDA-side switch table" of the hot path: ``expand`` evaluates every ``Next``
+disjunct/binding of the spec on one packed state and hands each successor to a sink,
+``first_violated_invariant`` / ``in_model`` evaluate the cfg's INVARIANTs / CONSTRAINTs.  The same
+header compiles for the device (engine kernels) and for the host (init-state packing checks and
+the CPU-side self-tests of the lowering).
+"""
+from __future__ import annotations
+
+import copy
+import hashlib
+import json
+from dataclasses import dataclass, field
+
+from ..frontend.cfg import Config, ModelValue, parse_cfg
+from ..frontend.modules import ModuleContext, load_root
+from ..frontend.tla_parser import parse_expression_text
+from ..frontend.values import FnVal, fmt, sort_key
+from . import layout as L
+from .compiler import Closure, Lowerer, Marker, Thunk
+from .svals import LowerError, SLazy, is_atom_const, is_const, is_int_const
+
+LOWERING_VERSION = 1
+
+
+@dataclass
+class LoweredModel:
+    name: str
+    module: str
+    header: str
+    layout: dict
+    words: int
+    state_bits: int
+    init_states: list[list[int]]
+    actions: list[dict]
+    invariants: list[str]
+    constraints: list[str]
+    check_deadlock: bool
+    max_fanout: int
+    warnings: list[str] = field(default_factory=list)
+    digest: str = ""
+    lowerer: object = None
+    variables: list[str] = field(default_factory=list)
+
+    def meta(self) -> dict:
+        return {
+            "name": self.name, "module": self.module, "words": self.words, "state_bits": self.state_bits,
+            "init_states": [[str(w) for w in s] for s in self.init_states],
+            "actions": self.actions, "invariants": self.invariants, "constraints": self.constraints,
+            "check_deadlock": self.check_deadlock, "max_fanout": self.max_fanout,
+            "layout": self.layout, "digest": self.digest, "warnings": self.warnings,
+            "lowering_version": LOWERING_VERSION,
+        }
+
+    def decode_state(self, words) -> dict:
+        return self.lowerer.layout.py_unpack(words)
+
+    def state_text(self, words) -> str:
+        st = self.decode_state(words)
+        return "\n".join(f"/\\ {v} = {fmt(st[v])}" for v in self.variables)
+
+
+# ---------------------------------------------------------------------------
+# layout inference
+# ---------------------------------------------------------------------------
+class TypeInference:
+    def __init__(self, lw: Lowerer):
+        self.lw = lw
+        self.found: dict[str, list] = {}     # var -> [(steps, Ty)]
+
+    def type_from_setval(self, v) -> L.Ty:
+        lw = self.lw
+        if isinstance(v, SLazy):
+            if v.kind == "recset":
+                return L.TRec({f: self.type_from_setval(s) for f, s in v.a.items()})
+            if v.kind == "fnset":
+                keys = sorted((x for _, x in lw.set_items(v.a)), key=sort_key)
+                elem = self.type_from_setval(v.b)
+                return L.TFn(keys, [copy.deepcopy(elem) for _ in keys])
+            if v.kind == "powerset":
+                return L.TSet(self.type_from_setval(v.a))
+            if v.kind == "union":
+                return self.merge(self.type_from_setval(v.a), self.type_from_setval(v.b))
+            raise LowerError(f"unbounded set {v.kind} in a layout type: give the variable a bounded "
+                             f"type through a '\\* kspec: LAYOUT Op' operator")
+        if not isinstance(v, frozenset):
+            raise LowerError(f"layout type is not a constant set: {v!r}")
+        if not v:
+            raise LowerError("empty set used as a layout type")
+        ints = [x for x in v if is_int_const(x)]
+        atoms = [x for x in v if is_atom_const(x)]
+        recs = [x for x in v if isinstance(x, FnVal)]
+        sets = [x for x in v if isinstance(x, frozenset)]
+        parts: list[L.Ty] = []
+        if ints:
+            parts.append(L.TInt(min(ints), max(ints)))
+        if atoms:
+            for a in atoms:
+                lw.gid(a)
+            parts.append(L.TEnum(atoms, lw.gids))
+        if recs:
+            doms = {frozenset(r.domain()) for r in recs}
+            if len(doms) != 1:
+                raise LowerError("layout type mixes records/functions with different domains")
+            dom = sorted(next(iter(doms)), key=sort_key)
+            if all(isinstance(k, str) for k in dom):
+                parts.append(L.TRec({f: self.type_from_setval(frozenset(r.apply(f) for r in recs)) for f in dom}))
+            else:
+                parts.append(L.TFn(dom, [self.type_from_setval(frozenset(r.apply(k) for r in recs)) for k in dom]))
+        if sets:
+            universe = frozenset().union(*sets)
+            parts.append(L.TSet(self.type_from_setval(universe)))
+        if len(ints) + len(atoms) + len(recs) + len(sets) != len(v):
+            raise LowerError("unsupported element kind in a layout type")
+        return parts[0] if len(parts) == 1 else L.TUnion(sorted(parts, key=lambda t: t.kind()))
+
+    def merge(self, a: L.Ty, b: L.Ty) -> L.Ty:
+        if isinstance(a, L.TInt) and isinstance(b, L.TInt):
+            return L.TInt(min(a.lo, b.lo), max(a.hi, b.hi))
+        if isinstance(a, L.TEnum) and isinstance(b, L.TEnum):
+            return L.TEnum(list(dict.fromkeys(a.atoms + b.atoms)), self.lw.gids)
+        alts = []
+        for t in (a, b):
+            alts.extend(t.alts if isinstance(t, L.TUnion) else [t])
+        merged: dict[str, L.Ty] = {}
+        for t in alts:
+            k = t.kind()
+            if k in merged:
+                if k in ("int", "atom"):
+                    merged[k] = self.merge(merged[k], t)
+                else:
+                    raise LowerError(f"cannot merge two layout alternatives of kind {k}")
+            else:
+                merged[k] = t
+        out = sorted(merged.values(), key=lambda t: t.kind())
+        return out[0] if len(out) == 1 else L.TUnion(out)
+
+    def as_path(self, e, ctx, fm, env):
+        lw = self.lw
+        k = e[0]
+        if k == "id":
+            if e[1] in env:
+                v = env[e[1]]
+                if isinstance(v, Thunk):
+                    return self.as_path(v.expr, v.ctx, v.fm, v.env)
+                return None
+            r = ctx.resolve(e[1], fm)
+            if r is None:
+                return None
+            if r.kind == "var":
+                return (e[1], [])
+            if r.kind == "subst":
+                return self.as_path(r.expr, r.ctx, r.from_module, {})
+            return None
+        if k == "fnapp" and len(e[2]) == 1:
+            base = self.as_path(e[1], ctx, fm, env)
+            if base is None:
+                return None
+            try:
+                idx = lw.ev(e[2][0], ctx, fm, env, None)
+            except LowerError:
+                return None
+            if not is_const(idx):
+                return None
+            return (base[0], base[1] + [("idx", idx)])
+        if k == "dot":
+            base = self.as_path(e[1], ctx, fm, env)
+            if base is None:
+                return None
+            return (base[0], base[1] + [("fld", e[2])])
+        return None
+
+    def collect(self, e, ctx, fm, env):
+        lw = self.lw
+        k = e[0]
+        if k == "and":
+            for x in e[1]:
+                self.collect(x, ctx, fm, env)
+            return
+        if k == "let":
+            self.collect(e[2], ctx, fm, lw.let_env(e[1], ctx, fm, env))
+            return
+        if k == "quant" and e[1] == "A":
+            try:
+                binds = lw.bindings(e[2], ctx, fm, env, None)
+            except LowerError:
+                return                      # state-dependent domain: not a type conjunct
+            for g, env2 in binds:
+                if g is True:
+                    self.collect(e[3], ctx, fm, env2)
+            return
+        if k in ("id", "app", "inst"):
+            op = None
+            if not (k == "id" and e[1] in env and not isinstance(env[e[1]], Closure)):
+                try:
+                    op = lw.find_operator(e, ctx, fm, env)
+                except LowerError:
+                    op = None
+            if op is not None:
+                target, defctx, args = op
+                body, c2, fm2, env2 = lw.bind_call(target, defctx, args, ctx, fm, env)
+                self.collect(body, c2, fm2, env2)
+            return
+        if k == "binop" and e[1] in ("\\in", "\\subseteq"):
+            p = self.as_path(e[2], ctx, fm, env)
+            if p is None:
+                return
+            try:
+                sv = lw.ev(e[3], ctx, fm, env, None)
+            except LowerError:
+                return
+            ty = self.type_from_setval(sv)
+            if e[1] == "\\subseteq":
+                ty = L.TSet(ty)
+            self.found.setdefault(p[0], []).append((p[1], ty))
+
+    def variable_type(self, var: str) -> L.Ty:
+        cons = self.found.get(var, [])
+        whole = [t for steps, t in cons if not steps]
+        if whole:
+            return whole[0]
+        by_key: dict = {}
+        for steps, t in cons:
+            if len(steps) == 1 and steps[0][0] == "idx":
+                by_key.setdefault(steps[0][1], t)
+        if by_key:
+            keys = sorted(by_key, key=sort_key)
+            return L.TFn(keys, [by_key[k] for k in keys])
+        raise LowerError(
+            f"no layout type found for variable {var}: the layout operator must contain a conjunct "
+            f"'{var} \\in <finite type set>' (or '\\subseteq')")
+
+
+# ---------------------------------------------------------------------------
+def _init_states(lw: Lowerer, init_expr) -> list[dict]:
+    out: list[dict] = []
+
+    def rec(items, st):
+        if not items:
+            for v in lw.variables:
+                if v not in st:
+                    raise LowerError(f"Init leaves {v} unassigned")
+            out.append(st)
+            return
+        (e, ctx, fm, env), rest = items[0], items[1:]
+        k = e[0]
+        if k == "and":
+            rec([(x, ctx, fm, env) for x in e[1]] + rest, st)
+            return
+        if k == "or":
+            for x in e[1]:
+                rec([(x, ctx, fm, env)] + rest, st)
+            return
+        if k == "quant" and e[1] == "E":
+            for g, env2 in lw.bindings(e[2], ctx, fm, env, st):
+                if g is not True:
+                    raise LowerError("Init quantifies over a non-constant set")
+                rec([(e[3], ctx, fm, env2)] + rest, st)
+            return
+        if k == "let":
+            rec([(e[2], ctx, fm, lw.let_env(e[1], ctx, fm, env))] + rest, st)
+            return
+        if k in ("id", "app", "inst"):
+            op = None
+            if not (k == "id" and e[1] in env and not isinstance(env[e[1]], Closure)):
+                op = lw.find_operator(e, ctx, fm, env)
+            if op is not None:
+                target, defctx, args = op
+                rec([lw.bind_call(target, defctx, args, ctx, fm, env)] + rest, st)
+                return
+        if k == "binop" and e[1] in ("=", "\\in"):
+            v = lw.resolve_var(e[2], ctx, fm, env)
+            if v is not None and v not in st:
+                rhs = lw.ev(e[3], ctx, fm, env, st)
+                if e[1] == "=":
+                    if not is_const(rhs):
+                        raise LowerError(f"Init value of {v} is not a constant")
+                    rec(rest, {**st, v: rhs})
+                else:
+                    for g, x in lw.set_items(rhs):
+                        rec(rest, {**st, v: x})
+                return
+        c = lw.ev_bool(e, ctx, fm, env, st)
+        if c is True:
+            rec(rest, st)
+        elif c is not False:
+            raise LowerError("Init contains a non-constant condition")
+
+    rec([(init_expr, lw.root, None, {})], {})
+    return out
+
+
+def _resolve_init_next(lw: Lowerer):
+    cfg, root = lw.cfg, lw.root
+    if cfg.init and cfg.next:
+        return ("id", cfg.init), ("id", cfg.next)
+    if cfg.specification:
+        d = root.find_def(cfg.specification, None)
+        if d is None:
+            raise LowerError(f"SPECIFICATION {cfg.specification} not found")
+        found = {"init": None, "next": None}
+
+        def walk(e):
+            if e[0] == "and":
+                for x in e[1]:
+                    walk(x)
+            elif e[0] == "box" and e[1][0] == "actionbox":
+                found["next"] = e[1][1]
+            elif e[0] != "fair" and found["init"] is None:
+                found["init"] = e
+        walk(d.body)
+        if found["init"] is None or found["next"] is None:
+            raise LowerError("SPECIFICATION is not of the form Init /\\ [][Next]_vars")
+        return found["init"], found["next"]
+    raise LowerError("cfg needs INIT+NEXT or SPECIFICATION")
+
+
+HEADER_PROLOGUE = """\
+// AUTO-GENERATED by kafka_specification_b200.lower -- do not edit.
+// model   : {name}
+// module  : {module}
+// digest  : {digest}
+#pragma once
+#include <stdint.h>
+#ifndef KMC_HD
+#  ifdef __CUDACC__
+#    define KMC_HD __host__ __device__ __forceinline__
+#  else
+#    define KMC_HD inline
+#  endif
+#endif
+#ifndef KMC_FAIL_LAYOUT
+#  define KMC_FAIL_LAYOUT 1   /* a successor value does not fit the packed layout */
+#endif
+namespace kmc_model {{
+static constexpr int W = {words};
+static constexpr int STATE_BITS = {bits};
+static constexpr int NUM_ACTIONS = {num_actions};
+static constexpr int NUM_INVARIANTS = {num_invariants};
+static constexpr int NUM_CONSTRAINTS = {num_constraints};
+static constexpr int NUM_INIT = {num_init};
+static constexpr int MAX_FANOUT = {max_fanout};   /* static bound: emit sites in expand() */
+static constexpr bool CHECK_DEADLOCK = {check_deadlock};
+struct State {{ uint64_t w[W]; }};
+"""
+
+
+def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | None = None) -> LoweredModel:
+    cfg = parse_cfg(cfg_text)
+    root = load_root(module, search_dirs)
+    lw = Lowerer(root, cfg)
+    if cfg.symmetry or cfg.view or cfg.properties or cfg.action_constraints:
+        raise LowerError("SYMMETRY / VIEW / PROPERTY / ACTION_CONSTRAINT are not supported")
+
+    # ASSUMEs of the root module (TLC evaluates them once at start-up)
+    for a, mod in root.assumes:
+        if lw.ev_bool(a, root, mod, {}, None) is not True:
+            raise LowerError(f"ASSUME in module {mod} is not TRUE for this cfg")
+
+    # layout
+    layout_op = cfg.layout or "TypeOk"
+    d, dctx = lw.named_def(layout_op)
+    ti = TypeInference(lw)
+    ti.collect(d.body, dctx, d.module, {})
+    lay = L.Layout()
+    lay.variables = list(lw.variables)
+    for v in lw.variables:
+        ty = copy.deepcopy(ti.variable_type(v))
+        if v in cfg.capacities:
+            if not isinstance(ty, L.TSet):
+                raise LowerError(f"CAPACITY given for {v}, which is not a set")
+            cap = lw.ev(parse_expression_text(cfg.capacities[v]), root, None, {}, None)
+            if not is_int_const(cap) or cap < 0:
+                raise LowerError(f"CAPACITY {v} does not evaluate to a natural number")
+            ty = L.TSet(ty.elem, cap)
+        lay.var_types[v] = ty
+        ty.alloc(lay, v)
+    lay.finish()
+    lw.layout = lay
+
+    init_e, next_e = _resolve_init_next(lw)
+    inits = _init_states(lw, init_e)
+    if not inits:
+        raise LowerError("Init has no solution")
+    init_words = [lay.py_pack(st) for st in inits]
+    for st, wds in zip(inits, init_words):
+        if lay.py_unpack(wds) != st:
+            raise LowerError("layout round-trip of an initial state failed")
+
+    # expand()
+    lw.begin_function()
+    if next_e[0] == "id":
+        nd, nctx = lw.named_def(next_e[1])
+        start = [(nd.body, nctx, nd.module, {})]
+    else:
+        start = [(next_e, root, None, {})]
+    lw.gen_next(start, {}, None)
+    expand_lines = lw.cg.lines
+    max_fanout = lw.emit_sites
+
+    # invariants
+    lw.begin_function()
+    inv_lines_start = len(lw.cg.lines)
+    for i, inv in enumerate(cfg.invariants):
+        idf, ictx = lw.named_def(inv)
+        c = lw.ev_bool(idf.body, ictx, idf.module, {})
+        if c is False:
+            lw.cg.emit(f"return {i};")
+        elif c is not True:
+            lw.cg.emit(f"if (!({c.s})) return {i};")
+    inv_lines = lw.cg.lines[inv_lines_start:]
+
+    # constraints
+    lw.begin_function()
+    conds = []
+    for con in cfg.constraints:
+        cdf, cctx = lw.named_def(con)
+        conds.append(lw.ev_bool(cdf.body, cctx, cdf.module, {}))
+    c_all = lw.b_and(conds)
+    con_lines = list(lw.cg.lines)
+    con_lines.append(f"  return {lw.bstr(c_all)};")
+
+    name = name or module
+    body_digest = hashlib.sha256(("\n".join(expand_lines + inv_lines + con_lines) + cfg_text).encode()).hexdigest()[:16]
+    unpack = lw.unpack_lines()
+
+    parts = [HEADER_PROLOGUE.format(
+        name=name, module=module, digest=body_digest, words=lay.words, bits=lay.bits,
+        num_actions=max(1, len(lw.actions)), num_invariants=len(cfg.invariants),
+        num_constraints=len(cfg.constraints), num_init=len(init_words), max_fanout=max(1, max_fanout),
+        check_deadlock="true" if cfg.check_deadlock else "false")]
+    parts.append("static const uint64_t INIT_STATES[NUM_INIT][W] = {")
+    for wds in init_words:
+        parts.append("  {" + ", ".join(f"0x{w:x}ull" for w in wds) + "},")
+    parts.append("};")
+    parts.append("/* successor enumeration: sink.emit(const State&, int action) per successor; sink.fail(code) on a layout trap */")
+    parts.append("template <class Sink> KMC_HD void expand(const State& s, Sink& sink) {")
+    parts.extend(unpack)
+    parts.extend(expand_lines)
+    parts.append("}")
+    parts.append("/* index of the first violated INVARIANT of the cfg, or -1 */")
+    parts.append("KMC_HD int first_violated_invariant(const State& s) {")
+    parts.extend(unpack)
+    parts.extend(inv_lines)
+    parts.append("  return -1;")
+    parts.append("}")
+    parts.append("/* conjunction of the cfg's CONSTRAINTs */")
+    parts.append("KMC_HD bool in_model(const State& s) {")
+    parts.extend(unpack)
+    parts.extend(con_lines)
+    parts.append("}")
+    parts.append("}  // namespace kmc_model")
+    header = "\n".join(parts) + "\n"
+    header = header.replace("  const unsigned a", "  [[maybe_unused]] const unsigned a")
+
+    return LoweredModel(
+        name=name, module=module, header=header, layout=lay.describe(), words=lay.words,
+        state_bits=lay.bits, init_states=init_words, actions=lw.actions or [{"name": "Next", "module": module}],
+        invariants=list(cfg.invariants), constraints=list(cfg.constraints),
+        check_deadlock=cfg.check_deadlock, max_fanout=max(1, max_fanout), warnings=lw.warnings,
+        digest=body_digest, lowerer=lw, variables=list(lw.variables))
