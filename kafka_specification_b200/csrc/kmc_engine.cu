@@ -1,0 +1,1025 @@
+// kmc_engine.cu -- the BFS frontier-expansion engine, compiled once per lowered model:
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared \
+//        -Xcompiler -fPIC -include <model>.h kmc_engine.cu -o libkmc_<model>.so
+//
+// It replaces TLC's Worker next-state loop, FPSet and StateQueue:
+//
+//   k_expand  (K1)  one thread per frontier state: coalesced load of the packed state vector,
+//                   the lowered Next switch table (kmc_model::expand), one candidate row
+//                   (state words + parent/action word) per successor, bucketed by owner rank
+//                   = fingerprint high bits.  Row slots are claimed with warp-aggregated
+//                   atomics (one atomic per warp per emit site).
+//   k_insert  (K2)  one thread per candidate: 64-bit fingerprint, open-addressing hash set in
+//                   HBM with 32-byte buckets (4 fingerprints = one DRAM sector, read with two
+//                   128-bit loads), CAS insertion, warp ballot/popc compaction of the winners
+//                   into the state store (= next frontier), parent link, and (K3) invariant
+//                   evaluation on every new state and on every constraint-violating successor.
+//                   Violating states (rare, terminal) go to a small ring; the host reports the
+//                   one with the smallest fingerprint, so the counterexample is deterministic.
+//
+// HBM layout (per rank):   table  u64[2^table_log2]            fingerprints, 0 = empty
+//                          store  u64[max_states][W]           all distinct states, BFS order;
+//                                                              level k is a contiguous range
+//                          parent u64[max_states]              parent ref | action << 56
+//                          cand   u64[world][region_rows][W+1] successors of one frontier chunk
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device kmc_create fails with
+// KMC_E_NO_GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kspecmc.h"
+
+namespace M = kmc_model;
+using M::State;
+
+static constexpr int W = M::W;
+static constexpr int ROW = W + 1;
+static constexpr int MAX_WORLD = 8;
+static constexpr uint64_t NO_PARENT = 0x0000FFFFFFFFFFFFull;
+static constexpr uint64_t IDX_MASK = 0x000000FFFFFFFFFFull;
+static constexpr bool EXACT64 = (M::STATE_BITS <= 63);
+
+#define KMC_FAIL_TABLE_FULL 2
+#define KMC_FAIL_STORE_FULL 3
+#define KMC_FAIL_CAND_FULL 4
+
+// ----------------------------------------------------------------------------------------
+// fingerprints
+// ----------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// States of <= 63 bits get a *bijective* fingerprint (the set is then exact, not
+// probabilistic); wider states get a chained 64-bit mix (TLC's FP64 contract: collisions
+// possible with probability ~ n^2 / 2^65).  0 is reserved for "empty slot".
+__host__ __device__ __forceinline__ uint64_t fingerprint(const State& s) {
+  if (EXACT64) return fmix64(s.w[0] + 1);
+  uint64_t h = fmix64(s.w[0] + 0x9E3779B97F4A7C15ull);
+#pragma unroll
+  for (int i = 1; i < W; ++i) h = fmix64(h ^ (s.w[i] + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)));
+  return h ? h : 1;
+}
+
+__host__ __device__ __forceinline__ uint32_t owner_of(uint64_t fp, uint32_t world) {
+  return (uint32_t)(((fp >> 32) * (uint64_t)world) >> 32);
+}
+
+// ----------------------------------------------------------------------------------------
+// device-side counters
+// ----------------------------------------------------------------------------------------
+struct DevCounters {
+  unsigned long long cand_count[MAX_WORLD];
+  unsigned long long store_tail;
+  unsigned long long generated;
+  unsigned long long deadlocks;
+  unsigned long long out_of_model;
+  unsigned long long probes;
+  unsigned long long fail;
+  unsigned long long max_fanout_seen;
+  unsigned long long viol_count;         // rows claimed in the violator ring
+  unsigned long long action_counts[64];
+};
+
+// Violating states are rare and terminal, so they go to a small ring: W state words, the
+// parent/action word, the fingerprint and the invariant index (~0 = deadlock).  The host picks
+// the entry with the smallest fingerprint -> the reported counterexample is deterministic
+// (as long as the first violating level has <= VIOL_RING violators).
+static constexpr int VIOL_RING = 1024;
+static constexpr int VIOL_ROW = W + 3;
+
+struct Params {
+  uint64_t* table;
+  uint64_t bucket_mask;     // #buckets - 1
+  uint64_t* store;
+  uint64_t* parent;
+  uint64_t max_states;
+  uint64_t* cand;
+  uint64_t region_rows;
+  DevCounters* ctr;
+  uint64_t* viol_ring;
+  uint32_t rank, world;
+  uint32_t check_deadlock;
+  uint32_t count_actions;
+};
+
+__device__ __forceinline__ unsigned lane_id() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(r));
+  return r;
+}
+
+__device__ __noinline__ void record_violation(const Params& p, const State& s, uint64_t meta, uint64_t fp, uint64_t inv) {
+  unsigned long long slot = atomicAdd(&p.ctr->viol_count, 1ull);
+  if (slot >= (unsigned long long)VIOL_RING) return;
+  uint64_t* row = p.viol_ring + slot * VIOL_ROW;
+#pragma unroll
+  for (int k = 0; k < W; ++k) row[k] = s.w[k];
+  row[W] = meta;
+  row[W + 1] = fp;
+  row[W + 2] = inv;
+}
+
+// ----------------------------------------------------------------------------------------
+// K1: expand
+// ----------------------------------------------------------------------------------------
+struct CandSink {
+  const Params& p;
+  uint64_t parent_ref;
+  int n;
+  int failed;
+
+  __device__ __forceinline__ void emit(const State& s, int action) {
+    ++n;
+    uint32_t dest = 0;
+    if (p.world > 1) dest = owner_of(fingerprint(s), p.world);
+    // warp-aggregated slot claim: lanes that reached this emit site together and target the
+    // same owner share one atomic
+    unsigned active = __activemask();
+    unsigned peers = (p.world > 1) ? __match_any_sync(active, dest) : active;
+    unsigned lane = lane_id();
+    int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(&p.ctr->cand_count[dest], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+    if (pos >= p.region_rows) {
+      failed = KMC_FAIL_CAND_FULL;
+      return;
+    }
+    uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + pos) * ROW;
+#pragma unroll
+    for (int i = 0; i < W; ++i) row[i] = s.w[i];
+    row[W] = parent_ref | ((uint64_t)action << 56);
+    if (p.count_actions && action < 64) atomicAdd(&p.ctr->action_counts[action], 1ull);
+  }
+  __device__ __forceinline__ void fail(int code) { failed = code; }
+};
+
+__global__ void __launch_bounds__(128) k_expand(Params p, uint64_t first, uint64_t count) {
+  unsigned long long gen = 0, dead = 0;
+  unsigned maxfan = 0;
+  int failed = 0;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    State s;
+    const uint64_t* src = p.store + (first + i) * W;
+#pragma unroll
+    for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
+    CandSink sink{p, (first + i) | ((uint64_t)p.rank << 40), 0, 0};
+    M::expand(s, sink);
+    gen += sink.n;
+    if ((unsigned)sink.n > maxfan) maxfan = sink.n;
+    if (sink.failed) failed = sink.failed;
+    if (sink.n == 0) {
+      ++dead;
+      if (p.check_deadlock) record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+    }
+  }
+  // warp reduce the statistics, one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    gen += __shfl_xor_sync(0xffffffffu, gen, o);
+    dead += __shfl_xor_sync(0xffffffffu, dead, o);
+    maxfan = max(maxfan, __shfl_xor_sync(0xffffffffu, maxfan, o));
+    failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
+  }
+  if (lane_id() == 0) {
+    if (gen) atomicAdd(&p.ctr->generated, gen);
+    if (dead) atomicAdd(&p.ctr->deadlocks, dead);
+    if (maxfan) atomicMax(&p.ctr->max_fanout_seen, (unsigned long long)maxfan);
+    if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K2: fingerprint-set insert (+ K3 invariants)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 ld_bucket_half(const uint64_t* p) {
+  // L2-coherent 128-bit load, no L1 allocation: buckets are touched once per probe
+  ulonglong2 v;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+// returns 1 = inserted (new), 0 = already present, -1 = table full
+__device__ __forceinline__ int fpset_insert(uint64_t* table, uint64_t bucket_mask, uint64_t fp, unsigned& probes) {
+  uint64_t b = (fp ^ (fp >> 31)) & bucket_mask;
+  for (int attempt = 0; attempt < 512; ++attempt) {
+    uint64_t* base = table + (b << 2);
+    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
+    ++probes;
+    uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+    if (v[0] == fp || v[1] == fp || v[2] == fp || v[3] == fp) return 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v[k] == 0) {
+        unsigned long long old = atomicCAS((unsigned long long*)(base + k), 0ull, (unsigned long long)fp);
+        if (old == 0) return 1;
+        if (old == fp) return 0;
+        // another fingerprint took the slot: keep scanning (slots never empty again)
+      }
+    }
+    b = (b + 1) & bucket_mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int fpset_contains(const uint64_t* table, uint64_t bucket_mask, uint64_t fp) {
+  uint64_t b = (fp ^ (fp >> 31)) & bucket_mask;
+  for (int attempt = 0; attempt < 512; ++attempt) {
+    const uint64_t* base = table + (b << 2);
+    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
+    if (lo.x == fp || lo.y == fp || hi.x == fp || hi.y == fp) return 1;
+    if (lo.x == 0 || lo.y == 0 || hi.x == 0 || hi.y == 0) return 0;
+    b = (b + 1) & bucket_mask;
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, const unsigned long long* n_ptr,
+                                                 uint64_t n_fixed) {
+  const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+  const uint64_t n_round = (n + 31) & ~31ull;
+  unsigned probes = 0;
+  unsigned oom = 0;
+  int failed = 0;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool valid = i < n;
+    State s;
+    uint64_t meta = 0, fp = 0;
+    bool is_new = false, inmodel = false;
+    if (valid) {
+      const uint64_t* row = rows + i * ROW;
+#pragma unroll
+      for (int k = 0; k < W; ++k) s.w[k] = __ldcs(row + k);
+      meta = __ldcs(row + W);
+      inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
+      fp = fingerprint(s);
+      if (inmodel) {
+        int r = fpset_insert(p.table, p.bucket_mask, fp, probes);
+        if (r < 0) failed = KMC_FAIL_TABLE_FULL;
+        is_new = r > 0;
+      } else {
+        ++oom;
+      }
+      if (M::NUM_INVARIANTS > 0 && (is_new || !inmodel)) {
+        int inv = M::first_violated_invariant(s);
+        if (inv >= 0) record_violation(p, s, meta, fp, (uint64_t)inv);
+      }
+    }
+    // compaction of the winners into the state store (next frontier)
+    unsigned mask = __ballot_sync(0xffffffffu, is_new);
+    if (mask) {
+      unsigned lane = lane_id();
+      int leader = __ffs(mask) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(&p.ctr->store_tail, (unsigned long long)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (is_new) {
+        uint64_t idx = base + __popc(mask & ((1u << lane) - 1));
+        if (idx < p.max_states) {
+          uint64_t* dst = p.store + idx * W;
+#pragma unroll
+          for (int k = 0; k < W; ++k) dst[k] = s.w[k];
+          p.parent[idx] = meta;
+        } else {
+          failed = KMC_FAIL_STORE_FULL;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    probes += __shfl_xor_sync(0xffffffffu, probes, o);
+    oom += __shfl_xor_sync(0xffffffffu, oom, o);
+    failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
+  }
+  if (lane_id() == 0) {
+    if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
+    if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
+    if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
+  }
+}
+
+__global__ void k_fpset_put(uint64_t* table, uint64_t bucket_mask, const uint64_t* fps, uint64_t n, uint8_t* seen,
+                            DevCounters* ctr, int insert) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t fp = fps[i] ? fps[i] : 1;
+    if (insert) {
+      unsigned probes = 0;
+      int r = fpset_insert(table, bucket_mask, fp, probes);
+      if (r < 0) atomicCAS(&ctr->fail, 0ull, (unsigned long long)KMC_FAIL_TABLE_FULL);
+      if (r > 0) atomicAdd(&ctr->store_tail, 1ull);
+      seen[i] = r == 0;
+    } else {
+      seen[i] = (uint8_t)fpset_contains(table, bucket_mask, fp);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+struct LaunchRec {
+  int kind;  // 0 expand, 1 insert, 2 other
+  cudaEvent_t a, b;
+};
+
+struct Engine {
+  int device = 0;
+  int sms = 148;
+  uint32_t rank = 0, world = 1;
+  int table_log2 = 0;
+  uint64_t max_states = 0;
+  uint64_t cand_bytes = 0;
+  bool cont = false;
+  bool check_deadlock = M::CHECK_DEADLOCK;
+  bool timing = true;
+  bool count_actions = false;
+
+  uint64_t* table = nullptr;
+  uint64_t table_slots = 0;
+  uint64_t* store = nullptr;
+  uint64_t* parent = nullptr;
+  uint64_t* cand = nullptr;
+  uint64_t region_rows = 0;
+  uint64_t* recv = nullptr;
+  uint64_t recv_rows = 0;
+  DevCounters* ctr = nullptr;
+  uint64_t* viol_ring = nullptr;
+  cudaStream_t stream = nullptr;
+  uint64_t chunk_states = 0;
+
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  std::vector<LaunchRec> launches;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+  // results
+  mutable std::mutex mu;
+  kmc_stats_t stats{};
+  std::vector<uint64_t> widths;
+  std::vector<uint64_t> action_counts;
+  kmc_violation_t viol{};
+  std::vector<std::vector<uint64_t>> trace;
+  std::vector<uint32_t> trace_actions;
+  bool ran = false;
+  uint64_t level_first = 0, level_count = 0;   // shard API
+  uint64_t shard_levels = 0;
+  std::string last_error;
+
+  Params params() const {
+    Params p;
+    p.table = table;
+    p.bucket_mask = (table_slots >> 2) - 1;
+    p.store = store;
+    p.parent = parent;
+    p.max_states = max_states;
+    p.cand = cand;
+    p.region_rows = region_rows;
+    p.ctr = ctr;
+    p.viol_ring = viol_ring;
+    p.rank = rank;
+    p.world = world;
+    p.check_deadlock = check_deadlock ? 1 : 0;
+    p.count_actions = count_actions ? 1 : 0;
+    return p;
+  }
+};
+
+struct kmcm_ctx {
+  Engine e;
+};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      E.last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                                 \
+      return (_e == cudaErrorMemoryAllocation) ? KMC_E_OOM : KMC_E_CUDA;                                 \
+    }                                                                                                    \
+  } while (0)
+
+static bool json_find(const char* js, const char* key, const char** val) {
+  if (!js) return false;
+  std::string pat = std::string("\"") + key + "\"";
+  const char* p = strstr(js, pat.c_str());
+  if (!p) return false;
+  p += pat.size();
+  while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+  if (*p != ':') return false;
+  ++p;
+  while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+  *val = p;
+  return true;
+}
+static bool json_num(const char* js, const char* key, double* out) {
+  const char* v;
+  if (!json_find(js, key, &v)) return false;
+  char* end;
+  double d = strtod(v, &end);
+  if (end == v) return false;
+  *out = d;
+  return true;
+}
+static bool json_bool(const char* js, const char* key, bool* out) {
+  const char* v;
+  if (!json_find(js, key, &v)) return false;
+  if (!strncmp(v, "true", 4)) { *out = true; return true; }
+  if (!strncmp(v, "false", 5)) { *out = false; return true; }
+  double d;
+  if (json_num(js, key, &d)) { *out = d != 0; return true; }
+  return false;
+}
+
+static cudaEvent_t get_event(Engine& E) {
+  if (E.events_used == E.event_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    E.event_pool.push_back(ev);
+  }
+  return E.event_pool[E.events_used++];
+}
+
+struct TimedLaunch {
+  Engine& E;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  TimedLaunch(Engine& e, int k) : E(e), kind(k) {
+    if (E.timing) {
+      a = get_event(E);
+      b = get_event(E);
+      cudaEventRecord(a, E.stream);
+    }
+  }
+  ~TimedLaunch() {
+    if (E.timing) {
+      cudaEventRecord(b, E.stream);
+      E.launches.push_back({kind, a, b});
+    }
+  }
+};
+
+static int grid_for(const Engine& E, uint64_t n, int block, int per_sm) {
+  uint64_t g = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)E.sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int engine_alloc(Engine& E) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    E.last_error = "no CUDA device visible; this library has no CPU fallback";
+    return KMC_E_NO_GPU;
+  }
+  if (E.device >= ndev) {
+    E.last_error = "device index out of range";
+    return KMC_E_BADARG;
+  }
+  CK(cudaSetDevice(E.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, E.device));
+  E.sms = prop.multiProcessorCount;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (E.table_log2 == 0) {
+    // default: a quarter of free memory for the set, rounded down to a power of two, <= 2^31 slots
+    int lg = 20;
+    while (lg < 31 && ((size_t)8 << (lg + 1)) <= free_b / 4) ++lg;
+    E.table_log2 = lg;
+  }
+  E.table_slots = 1ull << E.table_log2;
+  if (E.max_states == 0) E.max_states = E.table_slots / 2;
+  if (E.cand_bytes == 0) E.cand_bytes = std::min<uint64_t>(free_b / 8, 4ull << 30);
+  uint64_t rows_total = E.cand_bytes / (ROW * 8);
+  E.region_rows = rows_total / E.world;
+  if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
+  E.chunk_states = std::max<uint64_t>(1, E.region_rows / M::MAX_FANOUT);
+  CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&E.table, E.table_slots * 8));
+  CK(cudaMalloc(&E.store, E.max_states * W * 8));
+  CK(cudaMalloc(&E.parent, E.max_states * 8));
+  CK(cudaMalloc(&E.cand, E.region_rows * E.world * ROW * 8));
+  if (E.world > 1) {
+    E.recv_rows = E.region_rows * E.world;
+    CK(cudaMalloc(&E.recv, E.recv_rows * ROW * 8));
+  }
+  CK(cudaMalloc(&E.ctr, sizeof(DevCounters)));
+  CK(cudaMalloc(&E.viol_ring, (size_t)VIOL_RING * VIOL_ROW * 8));
+  CK(cudaEventCreate(&E.ev_begin));
+  CK(cudaEventCreate(&E.ev_end));
+  return KMC_OK;
+}
+
+static int engine_reset(Engine& E) {
+  CK(cudaSetDevice(E.device));
+  CK(cudaMemsetAsync(E.table, 0, E.table_slots * 8, E.stream));
+  DevCounters h;
+  memset(&h, 0, sizeof(h));
+  CK(cudaMemcpyAsync(E.ctr, &h, sizeof(h), cudaMemcpyHostToDevice, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  E.events_used = 0;
+  E.launches.clear();
+  E.widths.clear();
+  E.trace.clear();
+  E.trace_actions.clear();
+  memset(&E.viol, 0, sizeof(E.viol));
+  E.viol.invariant = -1;
+  E.level_first = E.level_count = 0;
+  E.shard_levels = 0;
+  return KMC_OK;
+}
+
+static int read_counters(Engine& E, DevCounters* h) {
+  CK(cudaMemcpyAsync(h, E.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  return KMC_OK;
+}
+
+static int fail_to_error(unsigned long long f) {
+  switch (f) {
+    case 0: return KMC_OK;
+    case KMC_FAIL_LAYOUT: return KMC_E_LAYOUT_OVERFLOW;
+    case KMC_FAIL_TABLE_FULL: return KMC_E_TABLE_FULL;
+    case KMC_FAIL_STORE_FULL: return KMC_E_STORE_FULL;
+    default: return KMC_E_CUDA;
+  }
+}
+
+// writes the init states as candidate rows (one region per owner) -- host side, tiny
+static int seed_init(Engine& E) {
+  std::vector<uint64_t> rows[MAX_WORLD];
+  unsigned long long counts[MAX_WORLD] = {0};
+  for (int i = 0; i < M::NUM_INIT; ++i) {
+    State s;
+    memcpy(s.w, M::INIT_STATES[i], sizeof(s.w));
+    uint32_t d = E.world > 1 ? owner_of(fingerprint(s), E.world) : 0;
+    // every rank seeds the same init states but only rank 0 contributes them, so that the
+    // generated count and the exchange see each init state exactly once
+    if (E.rank != 0) continue;
+    for (int k = 0; k < W; ++k) rows[d].push_back(s.w[k]);
+    rows[d].push_back(NO_PARENT);
+    counts[d]++;
+  }
+  for (uint32_t d = 0; d < E.world; ++d) {
+    if (counts[d] == 0) continue;
+    if (counts[d] > E.region_rows) return KMC_E_OOM;
+    CK(cudaMemcpyAsync(E.cand + (uint64_t)d * E.region_rows * ROW, rows[d].data(), rows[d].size() * 8,
+                       cudaMemcpyHostToDevice, E.stream));
+  }
+  CK(cudaMemcpyAsync(E.ctr, counts, sizeof(counts), cudaMemcpyHostToDevice, E.stream));
+  unsigned long long gen = E.rank == 0 ? M::NUM_INIT : 0;
+  CK(cudaMemcpyAsync(&E.ctr->generated, &gen, sizeof(gen), cudaMemcpyHostToDevice, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  return KMC_OK;
+}
+
+static int launch_insert(Engine& E, const uint64_t* rows, const unsigned long long* n_dev, uint64_t n_fixed,
+                         uint64_t n_bound) {
+  Params p = E.params();
+  {
+    TimedLaunch t(E, 1);
+    k_insert<<<grid_for(E, n_bound, 256, 8), 256, 0, E.stream>>>(p, rows, n_dev, n_fixed);
+  }
+  CK(cudaGetLastError());
+  return KMC_OK;
+}
+
+static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
+  Params p = E.params();
+  TimedLaunch t(E, 0);
+  k_expand<<<grid_for(E, count, 128, 8), 128, 0, E.stream>>>(p, first, count);
+  CK(cudaGetLastError());
+  return KMC_OK;
+}
+
+static int reset_cand(Engine& E) {
+  CK(cudaMemsetAsync(E.ctr->cand_count, 0, sizeof(unsigned long long) * MAX_WORLD, E.stream));
+  return KMC_OK;
+}
+
+// Picks the violator with the smallest fingerprint (deadlocks, which belong to the level being
+// expanded, before invariant violations of the next level) and walks its parent links back to an
+// initial state.  `level` is the level being expanded (0 for the init insert).
+static int build_trace(Engine& E, const DevCounters& h, uint64_t level) {
+  uint64_t n = std::min<uint64_t>(h.viol_count, VIOL_RING);
+  if (n == 0) return KMC_OK;
+  std::vector<uint64_t> ring(n * VIOL_ROW);
+  CK(cudaMemcpy(ring.data(), E.viol_ring, ring.size() * 8, cudaMemcpyDeviceToHost));
+  const uint64_t* best = nullptr;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t* r = ring.data() + i * VIOL_ROW;
+    if (!best) { best = r; continue; }
+    bool r_dead = r[W + 2] == ~0ull, b_dead = best[W + 2] == ~0ull;
+    if (r_dead != b_dead) { if (r_dead) best = r; continue; }
+    if (r[W + 1] < best[W + 1] || (r[W + 1] == best[W + 1] && r[W] < best[W])) best = r;
+  }
+  std::vector<std::vector<uint64_t>> rev;
+  std::vector<uint32_t> rev_act;
+  uint64_t meta = best[W];
+  rev.push_back(std::vector<uint64_t>(best, best + W));
+  rev_act.push_back((uint32_t)(meta >> 56));
+  uint64_t guard = 0;
+  while ((meta & 0x0000FFFFFFFFFFFFull) != NO_PARENT && guard++ < 100000) {
+    uint64_t idx = meta & IDX_MASK;
+    uint32_t prank = (uint32_t)((meta >> 40) & 0xFF);
+    if (prank != E.rank || idx >= E.max_states) break;  // parent lives on another rank
+    std::vector<uint64_t> st(W);
+    CK(cudaMemcpy(st.data(), E.store + idx * W, W * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&meta, E.parent + idx, 8, cudaMemcpyDeviceToHost));
+    rev.push_back(st);
+    rev_act.push_back((uint32_t)(meta >> 56));
+  }
+  E.trace.assign(rev.rbegin(), rev.rend());
+  E.trace_actions.assign(rev_act.rbegin(), rev_act.rend());
+  bool dead = best[W + 2] == ~0ull;
+  E.viol.kind = dead ? KMC_RESULT_DEADLOCK : KMC_RESULT_INVARIANT;
+  E.viol.invariant = dead ? -1 : (int32_t)best[W + 2];
+  E.viol.level = dead ? level : level + 1;
+  E.viol.trace_len = E.trace.size();
+  E.viol.fingerprint = best[W + 1];
+  return KMC_OK;
+}
+
+static void accumulate_timing(Engine& E, kmc_stats_t& st) {
+  st.gpu_ms_expand = st.gpu_ms_insert = 0;
+  st.launches_expand = st.launches_insert = st.launches_other = 0;
+  for (const LaunchRec& r : E.launches) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.kind == 0) { st.gpu_ms_expand += ms; st.launches_expand++; }
+    else if (r.kind == 1) { st.gpu_ms_insert += ms; st.launches_insert++; }
+    else st.launches_other += 3;
+  }
+}
+
+static int engine_run(Engine& E) {
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = engine_reset(E);
+  if (rc) return rc;
+  if (E.world != 1) {
+    E.last_error = "kmc_run drives one rank; use the kmc_shard_* calls for world > 1";
+    return KMC_E_BADARG;
+  }
+  CK(cudaEventRecord(E.ev_begin, E.stream));
+  rc = seed_init(E);
+  if (rc) return rc;
+  rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, M::NUM_INIT);
+  if (rc) return rc;
+  DevCounters h;
+  rc = read_counters(E, &h);
+  if (rc) return rc;
+  uint64_t level_first = 0, level_end = h.store_tail, level = 1;
+  bool stopped = false;
+  int err = fail_to_error(h.fail);
+  if (!err && h.viol_count) {
+    build_trace(E, h, 0);
+    if (!E.cont) stopped = true;
+  }
+  while (!err && !stopped && level_end > level_first) {
+    E.widths.push_back(level_end - level_first);
+    for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
+      uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+      if ((rc = reset_cand(E))) return rc;
+      if ((rc = launch_expand(E, off, cnt))) return rc;
+      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)M::MAX_FANOUT))) return rc;
+    }
+    if ((rc = read_counters(E, &h))) return rc;
+    err = fail_to_error(h.fail);
+    {
+      std::lock_guard<std::mutex> g(E.mu);
+      E.stats.distinct = std::min<uint64_t>(h.store_tail, E.max_states);
+      E.stats.generated = h.generated;
+      E.stats.depth = level;
+      E.stats.queue = h.store_tail - level_end;
+    }
+    if (!err && h.viol_count && E.viol.kind == KMC_RESULT_OK) {
+      build_trace(E, h, level);
+      if (!E.cont) {
+        stopped = true;
+        level_first = level_end;
+        level_end = h.store_tail;
+        break;
+      }
+    }
+    level_first = level_end;
+    level_end = h.store_tail;
+    ++level;
+  }
+  CK(cudaEventRecord(E.ev_end, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  float total_ms = 0;
+  cudaEventElapsedTime(&total_ms, E.ev_begin, E.ev_end);
+  auto t1 = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> g(E.mu);
+    kmc_stats_t& st = E.stats;
+    st.distinct = std::min<uint64_t>(h.store_tail, E.max_states);
+    st.generated = h.generated;
+    st.queue = stopped ? (level_end - level_first) : 0;
+    st.depth = E.widths.size();
+    st.deadlocks = h.deadlocks;
+    st.out_of_model = h.out_of_model;
+    st.probes = h.probes;
+    st.levels = E.widths.size();
+    st.gpu_ms_total = total_ms;
+    st.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    st.table_slots = E.table_slots;
+    st.max_states = E.max_states;
+    st.complete = (!err && !stopped) ? 1 : 0;
+    if (E.timing) accumulate_timing(E, st);
+    E.action_counts.assign(h.action_counts, h.action_counts + 64);
+    E.ran = true;
+  }
+  return err;
+}
+
+// ----------------------------------------------------------------------------------------
+// exported per-model ABI (the dispatcher libkspecmc.so forwards kmc_* to these)
+// ----------------------------------------------------------------------------------------
+#define E (c->e)
+extern "C" {
+
+int kmcm_create(const char* options_json, kmcm_ctx** out) {
+  if (!out) return KMC_E_BADARG;
+  kmcm_ctx* c = new kmcm_ctx();
+  double d;
+  bool b;
+  if (json_num(options_json, "device", &d)) E.device = (int)d;
+  if (json_num(options_json, "table_log2", &d)) E.table_log2 = (int)d;
+  if (json_num(options_json, "max_states", &d)) E.max_states = (uint64_t)d;
+  if (json_num(options_json, "cand_bytes", &d)) E.cand_bytes = (uint64_t)d;
+  if (json_num(options_json, "rank", &d)) E.rank = (uint32_t)d;
+  if (json_num(options_json, "world", &d)) E.world = (uint32_t)d;
+  if (json_bool(options_json, "continue", &b)) E.cont = b;
+  if (json_bool(options_json, "check_deadlock", &b)) E.check_deadlock = b;
+  if (json_bool(options_json, "timing", &b)) E.timing = b;
+  if (json_bool(options_json, "count_actions", &b)) E.count_actions = b;
+  if (E.world < 1 || E.world > MAX_WORLD || E.rank >= E.world || (E.table_log2 && (E.table_log2 < 4 || E.table_log2 > 34))) {
+    delete c;
+    return KMC_E_BADARG;
+  }
+  int rc = engine_alloc(E);
+  *out = c;   // returned even on failure so that the caller can read the error text
+  if (rc == KMC_OK) rc = engine_reset(E);
+  return rc;
+}
+
+void kmcm_destroy(kmcm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(E.device);
+  cudaFree(E.table);
+  cudaFree(E.store);
+  cudaFree(E.parent);
+  cudaFree(E.cand);
+  cudaFree(E.recv);
+  cudaFree(E.ctr);
+  cudaFree(E.viol_ring);
+  for (cudaEvent_t ev : E.event_pool) cudaEventDestroy(ev);
+  if (E.ev_begin) cudaEventDestroy(E.ev_begin);
+  if (E.ev_end) cudaEventDestroy(E.ev_end);
+  if (E.stream) cudaStreamDestroy(E.stream);
+  delete c;
+}
+
+int kmcm_model_info(const kmcm_ctx*, kmc_model_info_t* out) {
+  if (!out) return KMC_E_BADARG;
+  memset(out, 0, sizeof(*out));
+  out->words = W;
+  out->state_bits = M::STATE_BITS;
+  out->num_actions = M::NUM_ACTIONS;
+  out->num_invariants = M::NUM_INVARIANTS;
+  out->num_init = M::NUM_INIT;
+  out->max_fanout = M::MAX_FANOUT;
+  out->check_deadlock = M::CHECK_DEADLOCK;
+  out->exact = EXACT64 ? 1 : 0;
+  strncpy(out->name, KMC_MODEL_NAME, sizeof(out->name) - 1);
+  strncpy(out->digest, KMC_MODEL_DIGEST, sizeof(out->digest) - 1);
+  return KMC_OK;
+}
+
+int kmcm_run(kmcm_ctx* c) {
+  if (!c) return KMC_E_BADARG;
+  return engine_run(E);
+}
+
+int kmcm_stats(const kmcm_ctx* c, kmc_stats_t* out) {
+  if (!c || !out) return KMC_E_BADARG;
+  std::lock_guard<std::mutex> g(E.mu);
+  *out = E.stats;
+  return KMC_OK;
+}
+
+int kmcm_level_widths(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) {
+  if (!c || !n) return KMC_E_BADARG;
+  std::lock_guard<std::mutex> g(E.mu);
+  *n = E.widths.size();
+  for (size_t i = 0; i < E.widths.size() && i < cap; ++i) out[i] = E.widths[i];
+  return KMC_OK;
+}
+
+int kmcm_action_counts(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) {
+  if (!c || !n) return KMC_E_BADARG;
+  std::lock_guard<std::mutex> g(E.mu);
+  *n = std::min<size_t>(M::NUM_ACTIONS, E.action_counts.size());
+  for (size_t i = 0; i < *n && i < cap; ++i) out[i] = E.action_counts[i];
+  return KMC_OK;
+}
+
+int kmcm_violation(const kmcm_ctx* c, kmc_violation_t* out) {
+  if (!c || !out) return KMC_E_BADARG;
+  if (!E.ran && E.shard_levels == 0) return KMC_E_STATE;
+  *out = E.viol;
+  return KMC_OK;
+}
+
+int kmcm_trace_state(const kmcm_ctx* c, uint32_t i, uint64_t* buf, size_t cap_words, uint32_t* action_id) {
+  if (!c || !buf) return KMC_E_BADARG;
+  if (i >= E.trace.size() || cap_words < (size_t)W) return KMC_E_BADARG;
+  memcpy(buf, E.trace[i].data(), W * 8);
+  if (action_id) *action_id = E.trace_actions[i];
+  return KMC_OK;
+}
+
+int kmcm_copy_states(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64_t* buf) {
+  kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
+  if (!c || !buf) return KMC_E_BADARG;
+  if (first + count > E.max_states) return KMC_E_BADARG;
+  CK(cudaSetDevice(E.device));
+  CK(cudaMemcpy(buf, E.store + first * W, count * W * 8, cudaMemcpyDeviceToHost));
+  return KMC_OK;
+}
+
+const char* kmcm_strerror(const kmcm_ctx* c, int code) {
+  switch (code) {
+    case KMC_OK: return "ok";
+    case KMC_E_BADARG: return (c && !E.last_error.empty()) ? E.last_error.c_str() : "bad argument";
+    case KMC_E_CUDA: return (c && !E.last_error.empty()) ? E.last_error.c_str() : "CUDA error";
+    case KMC_E_OOM: return "out of device memory";
+    case KMC_E_TABLE_FULL: return "fingerprint set is full (raise table_log2)";
+    case KMC_E_STORE_FULL: return "state store is full (raise max_states)";
+    case KMC_E_LAYOUT_OVERFLOW: return "a successor value does not fit the packed state layout";
+    case KMC_E_MODEL: return "cannot load the lowered model library";
+    case KMC_E_STATE: return "call sequence error";
+    case KMC_E_NO_GPU: return "no CUDA device visible; this library has no CPU fallback";
+    default: return "unknown error";
+  }
+}
+
+// ---- fingerprint set alone ---------------------------------------------------------------
+static int fpset_call(kmcm_ctx* c, const uint64_t* fps, size_t n, uint8_t* out, int insert) {
+  if (!c || (!fps && n) || (!out && n)) return KMC_E_BADARG;
+  if (n == 0) return KMC_OK;
+  CK(cudaSetDevice(E.device));
+  uint64_t* d_fps = nullptr;
+  uint8_t* d_out = nullptr;
+  CK(cudaMalloc(&d_fps, n * 8));
+  CK(cudaMalloc(&d_out, n));
+  CK(cudaMemcpyAsync(d_fps, fps, n * 8, cudaMemcpyHostToDevice, E.stream));
+  k_fpset_put<<<grid_for(E, n, 256, 8), 256, 0, E.stream>>>(E.table, (E.table_slots >> 2) - 1, d_fps, n, d_out, E.ctr, insert);
+  CK(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  cudaFree(d_fps);
+  cudaFree(d_out);
+  unsigned long long f = 0;
+  CK(cudaMemcpy(&f, &E.ctr->fail, 8, cudaMemcpyDeviceToHost));
+  return fail_to_error(f);
+}
+int kmcm_fpset_put(kmcm_ctx* c, const uint64_t* fps, size_t n, uint8_t* out_seen) { return fpset_call(c, fps, n, out_seen, 1); }
+int kmcm_fpset_contains(kmcm_ctx* c, const uint64_t* fps, size_t n, uint8_t* out) { return fpset_call(c, fps, n, out, 0); }
+int kmcm_fpset_size(const kmcm_ctx* c_, uint64_t* out) {
+  kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
+  if (!c || !out) return KMC_E_BADARG;
+  unsigned long long t = 0;
+  CK(cudaSetDevice(E.device));
+  CK(cudaMemcpy(&t, &E.ctr->store_tail, 8, cudaMemcpyDeviceToHost));
+  *out = t;
+  return KMC_OK;
+}
+
+// ---- sharded (multi-rank) building blocks -------------------------------------------------
+int kmcm_shard_begin(kmcm_ctx* c) {
+  if (!c) return KMC_E_BADARG;
+  int rc = engine_reset(E);
+  if (rc) return rc;
+  E.shard_levels = 0;
+  E.ran = false;
+  CK(cudaEventRecord(E.ev_begin, E.stream));
+  return KMC_OK;
+}
+
+int kmcm_shard_buffers(kmcm_ctx* c, kmc_shard_buffers_t* out) {
+  if (!c || !out) return KMC_E_BADARG;
+  out->cand = E.cand;
+  out->region_rows = E.region_rows;
+  out->cand_counts = (uint64_t*)E.ctr->cand_count;
+  out->recv = E.world > 1 ? E.recv : E.cand;
+  out->recv_rows_cap = E.world > 1 ? E.recv_rows : E.region_rows;
+  out->row_words = ROW;
+  return KMC_OK;
+}
+
+int kmcm_shard_seed_init(kmcm_ctx* c) {
+  if (!c) return KMC_E_BADARG;
+  return seed_init(E);
+}
+
+int kmcm_shard_expand(kmcm_ctx* c, uint64_t first, uint64_t count) {
+  if (!c) return KMC_E_BADARG;
+  if (count > E.chunk_states) {
+    E.last_error = "expand chunk larger than chunk_states";
+    return KMC_E_BADARG;
+  }
+  if (count == 0) return KMC_OK;
+  return launch_expand(E, first, count);
+}
+
+int kmcm_shard_counts(kmcm_ctx* c, uint64_t* host_counts) {
+  if (!c || !host_counts) return KMC_E_BADARG;
+  unsigned long long tmp[MAX_WORLD];
+  CK(cudaMemcpyAsync(tmp, E.ctr->cand_count, sizeof(tmp), cudaMemcpyDeviceToHost, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  for (uint32_t d = 0; d < E.world; ++d) host_counts[d] = tmp[d];
+  return KMC_OK;
+}
+
+int kmcm_shard_reset_cand(kmcm_ctx* c) {
+  if (!c) return KMC_E_BADARG;
+  return reset_cand(E);
+}
+
+int kmcm_shard_insert(kmcm_ctx* c, const uint64_t* rows_dev, uint64_t rows, uint64_t* new_tail) {
+  if (!c) return KMC_E_BADARG;
+  if (rows) {
+    int rc = launch_insert(E, rows_dev, nullptr, rows, rows);
+    if (rc) return rc;
+  }
+  if (new_tail) {
+    DevCounters h;
+    int rc = read_counters(E, &h);
+    if (rc) return rc;
+    *new_tail = h.store_tail;
+    return fail_to_error(h.fail);
+  }
+  return KMC_OK;
+}
+
+int kmcm_shard_level_done(kmcm_ctx* c, uint64_t* level_first, uint64_t* level_count) {
+  if (!c) return KMC_E_BADARG;
+  DevCounters h;
+  int rc = read_counters(E, &h);
+  if (rc) return rc;
+  uint64_t prev_end = E.level_first + E.level_count;
+  E.level_first = prev_end;
+  E.level_count = h.store_tail - prev_end;
+  E.shard_levels++;
+  if (level_first) *level_first = E.level_first;
+  if (level_count) *level_count = E.level_count;
+  {
+    std::lock_guard<std::mutex> g(E.mu);
+    E.stats.distinct = h.store_tail;
+    E.stats.generated = h.generated;
+    E.stats.deadlocks = h.deadlocks;
+    E.stats.out_of_model = h.out_of_model;
+    E.stats.probes = h.probes;
+    E.stats.table_slots = E.table_slots;
+    E.stats.max_states = E.max_states;
+    if (E.level_count) E.widths.push_back(E.level_count);
+    E.stats.levels = E.stats.depth = E.widths.size();
+  }
+  if (h.viol_count && E.viol.kind == KMC_RESULT_OK) build_trace(E, h, E.shard_levels - 1);
+  return fail_to_error(h.fail);
+}
+
+int kmcm_shard_sync(kmcm_ctx* c) {
+  if (!c) return KMC_E_BADARG;
+  CK(cudaEventRecord(E.ev_end, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  float total_ms = 0;
+  cudaEventElapsedTime(&total_ms, E.ev_begin, E.ev_end);
+  std::lock_guard<std::mutex> g(E.mu);
+  E.stats.gpu_ms_total = total_ms;
+  if (E.timing) accumulate_timing(E, E.stats);
+  return KMC_OK;
+}
+
+}  // extern "C"

@@ -333,6 +333,8 @@ HEADER_PROLOGUE = """\
 #ifndef KMC_FAIL_LAYOUT
 #  define KMC_FAIL_LAYOUT 1   /* a successor value does not fit the packed layout */
 #endif
+#define KMC_MODEL_NAME "{name}"
+#define KMC_MODEL_DIGEST "{digest}"
 namespace kmc_model {{
 static constexpr int W = {words};
 static constexpr int STATE_BITS = {bits};

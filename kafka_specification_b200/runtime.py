@@ -1,0 +1,374 @@
+"""ctypes binding of ``libkspecmc.so`` (include/kspecmc.h) -- the host side above the C ABI.
+
+Mirrors the reference-facing interface of the replaced path (TLC's ``ModelChecker``: run a
+model, read "states generated / distinct states / depth", fetch the error trace).  There is no
+CPU fallback: if the library, the lowered model or the GPU is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .frontend.cfg import ModelValue
+from .frontend.values import FnVal, fmt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build")
+
+KMC_ERRORS = {
+    0: "KMC_OK", -1: "KMC_E_BADARG", -2: "KMC_E_CUDA", -3: "KMC_E_OOM", -4: "KMC_E_TABLE_FULL",
+    -5: "KMC_E_STORE_FULL", -6: "KMC_E_LAYOUT_OVERFLOW", -7: "KMC_E_MODEL", -8: "KMC_E_STATE", -9: "KMC_E_NO_GPU",
+}
+
+
+class KmcError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"{KMC_ERRORS.get(code, code)}: {text}")
+        self.code = code
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("distinct", ctypes.c_uint64), ("generated", ctypes.c_uint64), ("queue", ctypes.c_uint64),
+        ("depth", ctypes.c_uint64), ("deadlocks", ctypes.c_uint64), ("out_of_model", ctypes.c_uint64),
+        ("probes", ctypes.c_uint64), ("levels", ctypes.c_uint64),
+        ("gpu_ms_total", ctypes.c_double), ("gpu_ms_expand", ctypes.c_double), ("gpu_ms_insert", ctypes.c_double),
+        ("launches_expand", ctypes.c_uint64), ("launches_insert", ctypes.c_uint64), ("launches_other", ctypes.c_uint64),
+        ("wall_ms", ctypes.c_double), ("table_slots", ctypes.c_uint64), ("max_states", ctypes.c_uint64),
+        ("complete", ctypes.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Violation(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("invariant", ctypes.c_int32), ("level", ctypes.c_uint64),
+                ("trace_len", ctypes.c_uint64), ("fingerprint", ctypes.c_uint64)]
+
+
+class ModelInfo(ctypes.Structure):
+    _fields_ = [("words", ctypes.c_int32), ("state_bits", ctypes.c_int32), ("num_actions", ctypes.c_int32),
+                ("num_invariants", ctypes.c_int32), ("num_init", ctypes.c_int32), ("max_fanout", ctypes.c_int32),
+                ("check_deadlock", ctypes.c_int32), ("exact", ctypes.c_int32),
+                ("name", ctypes.c_char * 128), ("digest", ctypes.c_char * 32)]
+
+
+class ShardBuffers(ctypes.Structure):
+    _fields_ = [("cand", ctypes.c_void_p), ("region_rows", ctypes.c_uint64), ("cand_counts", ctypes.c_void_p),
+                ("recv", ctypes.c_void_p), ("recv_rows_cap", ctypes.c_uint64), ("row_words", ctypes.c_int32)]
+
+
+_LIB = None
+
+
+def load_library(path: str | None = None) -> ctypes.CDLL:
+    """Loads libkspecmc.so; fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or os.path.join(BUILD, "libkspecmc.so")
+    if not os.path.exists(path):
+        raise KmcError(-7, f"{path} is missing: run `python -m kafka_specification_b200.build --all` "
+                           f"(there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, u64p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)
+    lib.kmc_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.kmc_destroy.argtypes = [vp]
+    lib.kmc_destroy.restype = None
+    lib.kmc_model_info.argtypes = [vp, ctypes.POINTER(ModelInfo)]
+    lib.kmc_run.argtypes = [vp]
+    lib.kmc_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.kmc_level_widths.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.kmc_action_counts.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.kmc_violation.argtypes = [vp, ctypes.POINTER(Violation)]
+    lib.kmc_trace_state.argtypes = [vp, ctypes.c_uint32, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
+    lib.kmc_copy_states.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.kmc_strerror.argtypes = [vp, ctypes.c_int]
+    lib.kmc_strerror.restype = ctypes.c_char_p
+    lib.kmc_fpset_put.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    lib.kmc_fpset_contains.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    lib.kmc_fpset_size.argtypes = [vp, u64p]
+    lib.kmc_shard_begin.argtypes = [vp]
+    lib.kmc_shard_buffers.argtypes = [vp, ctypes.POINTER(ShardBuffers)]
+    lib.kmc_shard_seed_init.argtypes = [vp]
+    lib.kmc_shard_expand.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64]
+    lib.kmc_shard_counts.argtypes = [vp, u64p]
+    lib.kmc_shard_reset_cand.argtypes = [vp]
+    lib.kmc_shard_insert.argtypes = [vp, vp, ctypes.c_uint64, u64p]
+    lib.kmc_shard_level_done.argtypes = [vp, u64p, u64p]
+    lib.kmc_shard_sync.argtypes = [vp]
+    for fn in ("kmc_create", "kmc_model_info", "kmc_run", "kmc_stats", "kmc_level_widths", "kmc_action_counts",
+               "kmc_violation", "kmc_trace_state", "kmc_copy_states", "kmc_fpset_put", "kmc_fpset_contains",
+               "kmc_fpset_size", "kmc_shard_begin", "kmc_shard_buffers", "kmc_shard_seed_init", "kmc_shard_expand",
+               "kmc_shard_counts", "kmc_shard_reset_cand", "kmc_shard_insert", "kmc_shard_level_done", "kmc_shard_sync"):
+        getattr(lib, fn).restype = ctypes.c_int
+    _LIB = lib
+    return lib
+
+
+def model_paths(name: str) -> tuple[str, str]:
+    d = os.path.join(BUILD, "models", name)
+    return os.path.join(d, f"libkmc_{name}.so"), os.path.join(d, "model.json")
+
+
+# ---------------------------------------------------------------------------
+# decoding packed states from model.json (no lowering needed at run time)
+# ---------------------------------------------------------------------------
+def _parse_atom(text: str):
+    if text.startswith('"'):
+        return text[1:-1]
+    try:
+        return int(text)
+    except ValueError:
+        return ModelValue(text)
+
+
+def _bits_for(card: int) -> int:
+    return max(0, (card - 1).bit_length())
+
+
+class StateDecoder:
+    """Rebuilds TLA+ values from packed words using the layout description in model.json."""
+
+    def __init__(self, meta: dict):
+        self.meta = meta
+        self.lay = meta["layout"]
+        self.atoms = self.lay["atoms"]
+        self.variables = self.lay["variables"]
+
+    def _card(self, t) -> int:
+        k = t["t"]
+        if k == "int":
+            return t["hi"] - t["lo"] + 1
+        if k == "enum":
+            return len(t["values"])
+        if k == "rec":
+            c = 1
+            for f in t["fields"].values():
+                c *= self._card(f)
+            return c
+        if k == "fn":
+            return self._card(t["elem"]) ** len(t["keys"])
+        if k == "union":
+            return sum(self._card(a) for a in t["alts"])
+        if k == "set":
+            return 1 << self._card(t["elem"])
+        raise ValueError(k)
+
+    def _dec(self, t, code: int):
+        k = t["t"]
+        if k == "int":
+            return code + t["lo"]
+        if k == "enum":
+            return _parse_atom(t["values"][code])
+        if k == "rec":
+            d = {}
+            for f, ft in t["fields"].items():
+                c = self._card(ft)
+                d[f] = self._dec(ft, code % c)
+                code //= c
+            return FnVal(d)
+        if k == "fn":
+            d = {}
+            c = self._card(t["elem"])
+            for key in t["keys"]:
+                d[_parse_atom(key)] = self._dec(t["elem"], code % c)
+                code //= c
+            return FnVal(d)
+        if k == "union":
+            off = 0
+            for a in t["alts"]:
+                c = self._card(a)
+                if code < off + c:
+                    return self._dec(a, code - off)
+                off += c
+            raise ValueError("bad union code")
+        if k == "set":
+            c = self._card(t["elem"])
+            return frozenset(self._dec(t["elem"], j) for j in range(c) if (code >> j) & 1)
+        raise ValueError(k)
+
+    def _read(self, t, codes: list[int], pos: list[int]):
+        k = t["t"]
+        if k == "rec":
+            return FnVal({f: self._read(ft, codes, pos) for f, ft in t["fields"].items()})
+        if k == "fn":
+            return FnVal({_parse_atom(key): self._read(t["elem"], codes, pos) for key in t["keys"]})
+        if k == "set":
+            ecard = self._card(t["elem"])
+            if t["repr"] == "bitmap":
+                out, base, n = [], 0, ecard
+                while n > 0:
+                    b = min(32, n)
+                    m = codes[pos[0]]
+                    pos[0] += 1
+                    out += [self._dec(t["elem"], base + j) for j in range(b) if (m >> j) & 1]
+                    base += b
+                    n -= b
+                return frozenset(out)
+            cnt = codes[pos[0]]
+            pos[0] += 1
+            slots = codes[pos[0]: pos[0] + t["cap"]]
+            pos[0] += t["cap"]
+            return frozenset(self._dec(t["elem"], c) for c in slots[:cnt])
+        card = self._card(t)
+        if _bits_for(card) == 0:
+            return self._dec(t, 0)
+        c = codes[pos[0]]
+        pos[0] += 1
+        return self._dec(t, c)
+
+    def decode(self, words) -> dict:
+        codes = [(int(words[a["word"]]) >> a["shift"]) & ((1 << a["bits"]) - 1) for a in self.atoms]
+        pos = [0]
+        return {v: self._read(self.lay["types"][v], codes, pos) for v in self.variables}
+
+    def text(self, words) -> str:
+        st = self.decode(words)
+        return "\n".join(f"/\\ {v} = {fmt(st[v])}" for v in self.variables)
+
+
+# ---------------------------------------------------------------------------
+@dataclass
+class RunResult:
+    distinct: int
+    generated: int
+    depth: int
+    queue: int
+    deadlocks: int
+    complete: bool
+    levels: list[int]
+    stats: dict
+    violation: dict | None = None
+    trace: list[dict] = field(default_factory=list)
+
+
+class Checker:
+    """One GPU-resident model checker instance (one ``kmc_ctx``)."""
+
+    def __init__(self, model: str, model_lib: str | None = None, model_json: str | None = None, **options):
+        self.lib = load_library()
+        lib_path, json_path = model_paths(model)
+        self.model_lib = model_lib or lib_path
+        json_path = model_json or json_path
+        if not os.path.exists(self.model_lib):
+            raise KmcError(-7, f"lowered model library {self.model_lib} is missing (build it first; no CPU fallback)")
+        with open(json_path) as f:
+            self.meta = json.load(f)
+        self.decoder = StateDecoder(self.meta)
+        self.ctx = ctypes.c_void_p()
+        opts = {("continue" if k == "cont" else k): v for k, v in options.items()}
+        rc = self.lib.kmc_create(self.model_lib.encode(), json.dumps(opts).encode(), ctypes.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.kmc_strerror(self.ctx, rc).decode() if self.ctx else "kmc_create failed"
+            if self.ctx:
+                self.lib.kmc_destroy(self.ctx)
+                self.ctx = None
+            raise KmcError(rc, msg)
+        self.info = ModelInfo()
+        self._check(self.lib.kmc_model_info(self.ctx, ctypes.byref(self.info)))
+        if self.info.digest.decode() != self.meta["digest"]:
+            raise KmcError(-7, "model.json does not belong to the loaded model library (digest mismatch)")
+        self.words = self.info.words
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KmcError(rc, self.lib.kmc_strerror(self.ctx, rc).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.kmc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- full BFS ------------------------------------------------------------
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self.lib.kmc_stats(self.ctx, ctypes.byref(st)))
+        return st.as_dict()
+
+    def level_widths(self) -> list[int]:
+        buf = (ctypes.c_uint64 * 4096)()
+        n = ctypes.c_size_t()
+        self._check(self.lib.kmc_level_widths(self.ctx, buf, 4096, ctypes.byref(n)))
+        return [int(buf[i]) for i in range(min(n.value, 4096))]
+
+    def action_counts(self) -> dict:
+        buf = (ctypes.c_uint64 * 64)()
+        n = ctypes.c_size_t()
+        self._check(self.lib.kmc_action_counts(self.ctx, buf, 64, ctypes.byref(n)))
+        return {a["name"]: int(buf[i]) for i, a in enumerate(self.meta["actions"]) if i < n.value}
+
+    def violation(self) -> dict | None:
+        v = Violation()
+        self._check(self.lib.kmc_violation(self.ctx, ctypes.byref(v)))
+        if v.kind == 0:
+            return None
+        return {"kind": "invariant" if v.kind == 1 else "deadlock",
+                "invariant": self.meta["invariants"][v.invariant] if v.kind == 1 else None,
+                "level": int(v.level), "trace_len": int(v.trace_len), "fingerprint": int(v.fingerprint)}
+
+    def trace(self) -> list[dict]:
+        v = self.violation()
+        if v is None:
+            return []
+        out = []
+        buf = (ctypes.c_uint64 * self.words)()
+        act = ctypes.c_uint32()
+        for i in range(v["trace_len"]):
+            self._check(self.lib.kmc_trace_state(self.ctx, i, buf, self.words, ctypes.byref(act)))
+            words = [int(buf[k]) for k in range(self.words)]
+            a = self.meta["actions"][act.value] if (i > 0 and act.value < len(self.meta["actions"])) else None
+            out.append({"words": words, "action": a, "state": self.decoder.decode(words),
+                        "text": self.decoder.text(words)})
+        return out
+
+    def run(self, raise_on_error: bool = True) -> RunResult:
+        rc = self.lib.kmc_run(self.ctx)
+        if rc != 0 and raise_on_error:
+            self._check(rc)
+        st = self.stats()
+        viol = self.violation()
+        return RunResult(distinct=st["distinct"], generated=st["generated"], depth=st["depth"], queue=st["queue"],
+                         deadlocks=st["deadlocks"], complete=bool(st["complete"]), levels=self.level_widths(),
+                         stats=st, violation=viol, trace=self.trace() if viol else [])
+
+    def copy_states(self, first: int, count: int) -> np.ndarray:
+        buf = np.empty((count, self.words), dtype=np.uint64)
+        if count:
+            self._check(self.lib.kmc_copy_states(self.ctx, first, count, buf.ctypes.data))
+        return buf
+
+    # -- fingerprint set alone (FPSet.put / contains / size) -----------------
+    def fpset_put(self, fps: np.ndarray) -> np.ndarray:
+        fps = np.ascontiguousarray(fps, dtype=np.uint64)
+        seen = np.zeros(len(fps), dtype=np.uint8)
+        self._check(self.lib.kmc_fpset_put(self.ctx, fps.ctypes.data, len(fps), seen.ctypes.data))
+        return seen.astype(bool)
+
+    def fpset_contains(self, fps: np.ndarray) -> np.ndarray:
+        fps = np.ascontiguousarray(fps, dtype=np.uint64)
+        out = np.zeros(len(fps), dtype=np.uint8)
+        self._check(self.lib.kmc_fpset_contains(self.ctx, fps.ctypes.data, len(fps), out.ctypes.data))
+        return out.astype(bool)
+
+    def fpset_size(self) -> int:
+        n = ctypes.c_uint64()
+        self._check(self.lib.kmc_fpset_size(self.ctx, ctypes.byref(n)))
+        return int(n.value)
