@@ -116,6 +116,7 @@ def compile_model(name: str, force: bool = False, verbose_ptxas: bool = True) ->
     if not force and os.path.exists(so) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return so
     cmd = [nvcc_path(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+           "-diag-suppress", "177",
            f"-I{INCLUDE}", "-include", hdr, os.path.join(CSRC, "kmc_engine.cu"), "-o", so]
     if verbose_ptxas:
         cmd[1:1] = ["-Xptxas", "-v"]
@@ -140,16 +141,31 @@ def registry() -> dict:
         return json.load(f)
 
 
-def build_all(force: bool = False, only: list[str] | None = None, verbose: bool = True) -> dict[str, str]:
+def build_all(force: bool = False, only: list[str] | None = None, verbose: bool = True, jobs: int = 0) -> dict[str, str]:
+    """Lower (sequentially, it is fast) and compile (in parallel: nvcc dominates) every registered model."""
+    from concurrent.futures import ThreadPoolExecutor
     build_dispatcher(force)
-    out = {}
+    todo = []
     for name, spec in registry().items():
         if only and name not in only:
             continue
+        module, cfg_path = spec["module"], os.path.join(ROOT, spec["cfg"])
+        have_sources = any(os.path.exists(os.path.join(d, module + ".tla")) for d in tla_search_dirs())
+        if have_sources:
+            lower_to_dir(module, cfg_path, name)
+        elif not os.path.exists(os.path.join(model_dir(name), "model.h")):
+            raise RuntimeError(f"{module}.tla is not reachable and build/models/{name}/model.h was not prebuilt")
+        todo.append(name)
+    jobs = jobs or min(8, os.cpu_count() or 1)
+
+    def one(name):
+        so = compile_model(name, force=force)
         if verbose:
-            print(f"[build] {name}: {spec['module']} + {spec['cfg']}", flush=True)
-        out[name] = build_model(spec["module"], os.path.join(ROOT, spec["cfg"]), name, force=force)
-    return out
+            print(f"[build] {name}: {so}", flush=True)
+        return name, so
+
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        return dict(ex.map(one, todo))
 
 
 def main(argv=None):

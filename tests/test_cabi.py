@@ -1,0 +1,97 @@
+"""The C-ABI library: loads, exports every symbol include/kspecmc.h declares, fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "kspecmc.h")
+LIB = os.path.join(ROOT, "build", "libkspecmc.so")
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(kmc_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from kafka_specification_b200 import build as B
+    B.build_dispatcher()
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ("kmc_create", "kmc_run", "kmc_stats", "kmc_violation", "kmc_trace_state", "kmc_strerror", "kmc_destroy",
+              "kmc_fpset_put", "kmc_fpset_contains", "kmc_fpset_size", "kmc_shard_expand", "kmc_shard_insert"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_model_libraries_export_the_per_model_abi():
+    models = os.path.join(ROOT, "build", "models")
+    if not os.path.isdir(models):
+        pytest.skip("models not built")
+    want = {s.replace("kmc_", "kmcm_", 1) for s in declared_symbols()}
+    n = 0
+    for name in os.listdir(models):
+        so = os.path.join(models, name, f"libkmc_{name}.so")
+        if not os.path.exists(so):
+            continue
+        out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+        have = set(re.findall(r"\bT (kmcm_[a-z_0-9]+)", out))
+        assert want <= have, (name, sorted(want - have))
+        n += 1
+    assert n > 0
+
+
+def test_model_library_is_sm100a_device_code():
+    so = os.path.join(ROOT, "build", "models", "kip320_small", "libkmc_kip320_small.so")
+    if not os.path.exists(so):
+        pytest.skip("model not built")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_bad_model_path_fails_loudly(lib):
+    lib.kmc_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.kmc_strerror.restype = ctypes.c_char_p
+    lib.kmc_strerror.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    ctx = ctypes.c_void_p()
+    rc = lib.kmc_create(b"/nonexistent/libkmc_x.so", b"{}", ctypes.byref(ctx))
+    assert rc == -7                                     # KMC_E_MODEL
+    assert b"cannot load" in lib.kmc_strerror(ctx, rc)
+    lib.kmc_destroy.argtypes = [ctypes.c_void_p]
+    lib.kmc_destroy(ctx)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a machine without a CUDA device the product path must refuse to run (KMC_E_NO_GPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    so = os.path.join(ROOT, "build", "models", "idsequence", "libkmc_idsequence.so")
+    if not os.path.exists(so):
+        pytest.skip("model not built")
+    from kafka_specification_b200.runtime import Checker, KmcError
+    with pytest.raises(KmcError) as e:
+        Checker("idsequence")
+    assert e.value.code == -9 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kafka_specification_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert "oracle" not in text.replace("Oracle A", "").replace("oracles", "").lower() or \
+                    "import" not in "".join(l for l in text.splitlines() if "oracle" in l.lower()), f

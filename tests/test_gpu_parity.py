@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path, through the C ABI, against the goldens and the C oracle.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+Nothing here reads /root/reference: models are prebuilt (build/models/*), goldens are committed
+(tests/golden/goldens.json), Oracle B compiles from oracle/ with gcc.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+ALL_MODELS = ["idsequence", "frl_tiny", "frl_3x4x2", "frl_3x4x3", "kip320_n2", "trunchw_n2", "kip101_n2", "kip279_n2",
+              "firsttry_n2", "kip320_small", "trunchw_small", "kip101_small", "kip279_small", "firsttry_small",
+              "asyncisr_v2", "asyncisr_small"]
+DIGEST_MODELS = ["idsequence", "frl_tiny", "kip320_n2", "trunchw_n2", "kip101_n2", "kip279_n2", "firsttry_n2",
+                 "asyncisr_v2", "asyncisr_small"]
+
+
+def checker(name, **kw):
+    from kafka_specification_b200.runtime import Checker
+    kw.setdefault("table_log2", 24)
+    return Checker(name, **kw)
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+def test_full_bfs_matches_golden(name, goldens):
+    """distinct / generated / depth / per-level widths / deadlocks bit-exact; search runs on past violations."""
+    g = goldens[name]
+    with checker(name, cont=True) as ck:
+        r = ck.run()
+    assert r.complete
+    assert (r.distinct, r.generated, r.depth, r.deadlocks) == (g["distinct"], g["generated"], g["depth"], g["deadlocks"])
+    assert r.levels == g["levels"]
+    assert r.queue == 0
+    inv_levels = {i: l for i, l in g["first_violation_level"].items() if l is not None}
+    if inv_levels:
+        assert r.violation is not None and r.violation["kind"] == "invariant"
+        assert r.violation["level"] == min(inv_levels.values())
+        assert inv_levels[r.violation["invariant"]] == r.violation["level"]
+        assert r.violation["trace_len"] == r.violation["level"]       # BFS counterexamples are shortest
+    else:
+        assert r.violation is None
+
+
+@pytest.mark.parametrize("name", DIGEST_MODELS)
+def test_state_set_matches_oracle_a_digest(name, goldens):
+    """Every reachable state, decoded to TLC text, matches the interpreter's set (order-independent digest)."""
+    from golden.make_golden import state_digest
+    g = goldens[name]
+    with checker(name, cont=True) as ck:
+        r = ck.run()
+        states = ck.copy_states(0, r.distinct)
+        texts = [ck.decoder.text(row) for row in states]
+    assert len(set(texts)) == g["distinct"]
+    assert state_digest(texts) == g["state_digest"]
+
+
+@pytest.mark.parametrize("name,params", [("kip320_small", ("kip320", [3, 2, 2, 2])),
+                                         ("firsttry_small", ("firsttry", [3, 2, 2, 2])),
+                                         ("frl_3x4x3", ("frl", [3, 4, 3]))])
+def test_against_oracle_b_live(name, params):
+    """The hand-written C restatement, run on the box's host cores, agrees with the GPU."""
+    import kso
+    ref = kso.run(params[0], params[1], max_states=4_000_000)
+    with checker(name, cont=True) as ck:
+        r = ck.run()
+    assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
+        ref["distinct"], ref["generated"], ref["depth"], ref["deadlocks"], ref["levels"])
+
+
+def test_stop_at_first_violation_and_trace():
+    """Default (no -continue): stop at the first violating level; the trace is a valid behaviour."""
+    with checker("trunchw_small") as ck:
+        r = ck.run()
+        assert not r.complete and r.violation["kind"] == "invariant"
+        assert r.violation["invariant"] in ("WeakIsr", "StrongIsr") and r.violation["level"] == 9
+        assert len(r.trace) == 9 and r.trace[0]["action"] is None
+        _assert_trace_is_behaviour("trunchw_small", r.trace, ck)
+        assert r.queue > 0
+
+
+def test_init_state_violation():
+    with checker("leaderinisr_init") as ck:
+        r = ck.run()
+    assert r.violation == {"kind": "invariant", "invariant": "LeaderInIsr", "level": 1, "trace_len": 1,
+                           "fingerprint": r.violation["fingerprint"]}
+    assert "quorumState = [isr |-> {r1, r2, r3}, leader |-> \"NONE\", leaderEpoch |-> -1]" in r.trace[0]["text"]
+
+
+def test_deadlock_detection_and_override():
+    with checker("idsequence_deadlock") as ck:
+        r = ck.run()
+        assert r.violation["kind"] == "deadlock" and r.violation["level"] == 6 and len(r.trace) == 6
+        assert [t["state"]["nextId"] for t in r.trace] == [0, 1, 2, 3, 4, 5]
+    with checker("idsequence_deadlock", check_deadlock=False) as ck:       # TLC's -deadlock switch
+        r = ck.run()
+        assert r.violation is None and r.complete and r.distinct == 6
+
+
+def test_rerun_is_deterministic_and_reusable():
+    with checker("kip279_small") as ck:
+        a = ck.run()
+        b = ck.run()
+    assert a.violation == b.violation                                 # min-fingerprint counterexample
+    assert [t["words"] for t in a.trace][-1] == [t["words"] for t in b.trace][-1]
+    assert (a.distinct, a.generated) == (b.distinct, b.generated)
+
+
+def test_table_full_and_store_full_are_reported():
+    from kafka_specification_b200.runtime import KmcError
+    with checker("kip320_small", table_log2=12, max_states=1 << 20) as ck:
+        with pytest.raises(KmcError) as e:
+            ck.run()
+        assert e.value.code == -4
+    with checker("kip320_small", table_log2=22, max_states=1000) as ck:
+        with pytest.raises(KmcError) as e:
+            ck.run()
+        assert e.value.code == -5
+
+
+def test_chunked_frontier_gives_identical_results(goldens):
+    """A tiny candidate buffer forces many expand/insert chunks per level."""
+    g = goldens["kip320_small"]
+    with checker("kip320_small", cand_bytes=8 << 20) as ck:
+        r = ck.run()
+    assert (r.distinct, r.generated, r.depth, r.levels) == (g["distinct"], g["generated"], g["depth"], g["levels"])
+    assert r.stats["launches_expand"] > 2 * g["depth"]
+
+
+def test_fpset_put_contains_size():
+    """TLC's FPSet contract: put() returns true iff the fingerprint was already present."""
+    rng = np.random.default_rng(7)
+    fps = rng.integers(1, 2**63, size=200_000, dtype=np.uint64)
+    with checker("idsequence", table_log2=20) as ck:
+        first = ck.fpset_put(fps[:100_000])
+        assert not first.any() or first.sum() == len(fps[:100_000]) - len(np.unique(fps[:100_000]))
+        again = ck.fpset_put(fps[:100_000])
+        assert again.all()
+        assert ck.fpset_contains(fps[:100_000]).all()
+        fresh = fps[100_000:]
+        fresh = fresh[~np.isin(fresh, fps[:100_000])]
+        assert not ck.fpset_contains(fresh).any()
+        assert ck.fpset_size() == len(np.unique(fps[:100_000]))
+        # duplicates inside one batch: exactly one of each pair is "new"
+        dup = np.concatenate([fresh[:1000], fresh[:1000]])
+        seen = ck.fpset_put(dup)
+        assert seen.sum() == 1000
+
+
+def test_probe_count_matches_generated(goldens):
+    """Hash-probe accounting used by the roofline: at load <= 0.5 about one 32 B bucket per candidate."""
+    with checker("kip320_small", table_log2=24) as ck:
+        r = ck.run()
+    assert r.generated <= r.stats["probes"] <= 1.05 * r.generated
+
+
+def _assert_trace_is_behaviour(name, trace, ck):
+    """Each step of the trace must be a successor of the previous state under the lowered Next,
+    checked with the host build of the same model header (g++ is available on the box)."""
+    import hashlib
+    hdr = os.path.join(ROOT, "build", "models", name, "model.h")
+    tag = hashlib.sha256(open(hdr, "rb").read()).hexdigest()[:12]
+    out = os.path.join(ROOT, "build", "hosttest")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, f"succ_{name}_{tag}.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f'-DKMC_MODEL_HEADER="{hdr}"',
+                               os.path.join(ROOT, "tests", "support", "host_succ.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.kmc_host_is_successor.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.kmc_host_is_init.argtypes = [ctypes.c_void_p]
+    w0 = np.array(trace[0]["words"], dtype=np.uint64)
+    assert lib.kmc_host_is_init(w0.ctypes.data) == 1
+    for a, b in zip(trace, trace[1:]):
+        wa = np.array(a["words"], dtype=np.uint64)
+        wb = np.array(b["words"], dtype=np.uint64)
+        act = lib.kmc_host_is_successor(wa.ctypes.data, wb.ctypes.data)
+        assert act >= 0, "trace step is not a successor"
+    wl = np.array(trace[-1]["words"], dtype=np.uint64)
+    lib.kmc_host_first_violated.argtypes = [ctypes.c_void_p]
+    assert lib.kmc_host_first_violated(wl.ctypes.data) >= 0
