@@ -1,0 +1,374 @@
+"""bench.py -- distinct states/sec of the BFS frontier-expansion path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete explicit-state BFS (Init -> empty frontier) of the headline model:
+Kip320 bound to KafkaReplication.tla, 3 brokers, LogSize ("MaxLogLen") 4 (models/Kip320.cfg).
+The input is the .cfg; there is no RNG.  The result of every step (distinct, generated, depth,
+per-level widths) is compared with the committed golden before a number is printed.
+
+  value        total distinct states / CUDA-event time of the level loop, state store and hash set
+               already allocated in HBM, max over ranks
+  e2e          the same through the C-ABI call a TLC-side caller makes (kmc_run + kmc_stats +
+               kmc_level_widths), wall clock: includes the hash-set reset, the host->device copy of the
+               initial states and the per-level device->host counter reads
+  roofline     dominant kernel by time, live CUDA-event launch durations (engine stream)
+  cpu_baseline Oracle B (oracle/kspec_oracle.c, "port": TLC itself cannot run here -- no JVM) on
+               the box's host cores, on a bounded prefix of the same BFS
+
+--impl reference times that CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_MODEL = "kip320_3x4_r3e3"
+METRIC = "distinct states/sec"
+
+
+def load_json(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = load_json(p)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def golden_for(model: str):
+    g = load_json(os.path.join(ROOT, "tests", "golden", "goldens.json"))
+    return g.get(model)
+
+
+def check_result(model, distinct, generated, depth, levels, deadlocks):
+    g = golden_for(model)
+    if g is None:
+        return "no golden committed for this model"
+    got = (distinct, generated, depth, deadlocks, levels)
+    want = (g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+    if got != want:
+        raise SystemExit(f"PARITY FAILURE on {model}: got {got[:4]}, golden {want[:4]}")
+    return "bit-exact vs tests/golden/goldens.json (" + "+".join(g["sources"]) + ")"
+
+
+def cpu_sample(model: str, seconds_budget: float = 20.0):
+    """Oracle B on a bounded prefix of the same BFS (the checker; never the thing shipped)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kso
+    reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
+    kmodel, params = reg["kso"]
+    cores = os.cpu_count() or 1
+    cap = 2_000_000
+    r = kso.run(kmodel, params, threads=cores, max_states=cap)
+    rate = r["distinct"] / max(r["seconds"], 1e-9)
+    # second, larger prefix sized for the budget (the first one also warms the page cache)
+    cap2 = int(min(max(rate * seconds_budget, cap), 60_000_000))
+    if cap2 > cap * 2:
+        r = kso.run(kmodel, params, threads=cores, max_states=cap2)
+    return {"value": r["distinct"] / max(r["seconds"], 1e-9), "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"Oracle B, first {r['distinct']} distinct states ({r['depth']} BFS levels) of {model}, "
+                      f"{r['seconds']:.1f} s on {cores} threads; TLC itself unavailable (no JVM)",
+            "seconds": r["seconds"], "distinct": r["distinct"]}
+
+
+def config_for(model: str, extra: dict | None = None) -> dict:
+    reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
+    c = {"workload": f"{reg['module']} ({reg['cfg']}): full BFS, KafkaReplication.tla 3 brokers LogSize 4, "
+                     f"kso params {reg['kso'][1]}",
+         "model": model, "l2": "inputs larger than L2: hash set and state store are GBs and the set is reset every step"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_reference(args):
+    """The reference-side CPU path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    sample = None
+    for i in range(args.warmup + args.steps):
+        s = cpu_sample(args.model, seconds_budget=8.0)
+        if i >= args.warmup:
+            vals.append(s)
+        sample = s
+    total_states = sum(v["distinct"] for v in vals)
+    total_s = sum(v["seconds"] for v in vals)
+    value = total_states / total_s
+    line = {"metric": METRIC, "value": value, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total_s / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic (the .cfg is the input)",
+            "impl": "reference", "config": config_for(args.model),
+            "cpu_baseline": {"value": value, "unit": "states/s", "cores": sample["cores"], "kind": "port",
+                             "sample": sample["sample"]},
+            "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_single(args):
+    import torch
+    from kafka_specification_b200.runtime import Checker
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    opts = {"device": dev}
+    if args.table_log2:
+        opts["table_log2"] = args.table_log2
+    if args.max_states:
+        opts["max_states"] = args.max_states
+    ck = Checker(args.model, **opts)
+    for _ in range(args.warmup):
+        ck.run()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    torch.cuda.synchronize()
+    gpu_ms, e2e_ms, launches = [], [], 0
+    exp_ms = ins_ms = 0.0
+    n_exp = n_ins = 0
+    res = None
+    t_bracket = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = ck.run()                         # kmc_run + kmc_stats + kmc_level_widths + kmc_violation
+        e2e_ms.append(1000.0 * (time.perf_counter() - t0))
+        st = res.stats
+        gpu_ms.append(st["gpu_ms_total"])
+        launches += st["launches_expand"] + st["launches_insert"] + st["launches_other"]
+        exp_ms += st["gpu_ms_expand"]
+        ins_ms += st["gpu_ms_insert"]
+        n_exp += st["launches_expand"]
+        n_ins += st["launches_insert"]
+    torch.cuda.synchronize()
+    bracket_ms = 1000.0 * (time.perf_counter() - t_bracket)
+    clocks = sampler.stop()
+    parity = check_result(args.model, res.distinct, res.generated, res.depth, res.levels, res.deadlocks)
+    if res.violation is not None or not res.complete:
+        raise SystemExit(f"bench: unexpected verdict {res.violation}")
+    W = ck.words
+    S = 8 * W
+    X, G, N = res.distinct, res.generated, res.distinct
+    steps = args.steps
+    value = steps * N / (sum(gpu_ms) / 1000.0)
+    e2e = steps * N / (sum(e2e_ms) / 1000.0)
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per BFS: expand reads X*S and writes G*(S+8); the hash probe
+    # reads G candidate rows' buckets (32 B each) and writes N*8 (slot) -- plus N*(S+8) store/parent
+    exp_bytes = X * S + G * (S + 8)
+    ins_bytes = G * 32 + N * 8
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = load_json(tp).get(args.model, {})
+
+    def roof(kernel, bytes_per_bfs, total_ms, n_launch):
+        sec = total_ms / 1000.0
+        ach = steps * bytes_per_bfs / sec / 1e9 if sec > 0 else 0.0
+        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(kernel), "peak_source": peak_src,
+                "avg_launch_ms": total_ms / max(1, n_launch), "launches": n_launch,
+                "algorithmic_bytes_per_launch": steps * bytes_per_bfs / max(1, n_launch),
+                "share_of_gpu_time": total_ms / max(1e-9, sum(gpu_ms))}
+
+    r_exp = roof("k_expand", exp_bytes, exp_ms, n_exp)
+    r_ins = roof("k_insert", ins_bytes, ins_ms, n_ins)
+    dominant, other = (r_exp, r_ins) if exp_ms >= ins_ms else (r_ins, r_exp)
+    cpu = cpu_sample(args.model) if not args.no_cpu_baseline else None
+    info = ck.info
+    depth = res.depth
+    line = {
+        "metric": METRIC, "value": value, "unit": "states/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": sum(gpu_ms) / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic (the .cfg is the input; no RNG)",
+        "config": config_for(args.model, {"distinct": N, "generated": G, "depth": depth, "state_words": W,
+                                          "table_slots": res.stats["table_slots"], "parity": parity,
+                                          "exact_fingerprints": bool(info.exact)}),
+        "roofline": dominant, "roofline_other": other,
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
+        "e2e": {"value": e2e, "unit": "states/s", "ms_per_step": sum(e2e_ms) / steps,
+                "h2d_bytes_per_step": info.num_init * (W + 1) * 8 + 8 * 16 + (depth + 1) * 64,
+                "d2h_bytes_per_step": (depth + 1) * (17 + 64) * 8 + 18 * 8 + depth * 8},
+        "bracket_ms_per_step": bracket_ms / steps,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    ck.close()
+    return 0
+
+
+def run_sharded(args):
+    import torch
+    import torch.distributed as dist
+    from kafka_specification_b200.sharded import CudaShardEngine, ShardedChecker
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    opts = {}
+    if args.table_log2:
+        opts["table_log2"] = args.table_log2
+    if args.max_states:
+        opts["max_states"] = args.max_states
+    eng = CudaShardEngine(args.model, rank, world, local, **opts)
+    drv = ShardedChecker(eng)
+    for _ in range(args.warmup):
+        drv.run()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    secs, gpu_ms, launches = [], [], 0
+    ins_ms = exp_ms = 0.0
+    n_ins = n_exp = 0
+    res = None
+    for _ in range(args.steps):
+        res = drv.run()                         # barrier inside; seconds = max over ranks
+        secs.append(res.seconds)
+        st = res.stats
+        gpu_ms.append(st["gpu_ms_total"])
+        launches += st["launches_expand"] + st["launches_insert"] + st["launches_other"]
+        exp_ms += st["gpu_ms_expand"]
+        ins_ms += st["gpu_ms_insert"]
+        n_exp += st["launches_expand"]
+        n_ins += st["launches_insert"]
+    dist.barrier()
+    torch.cuda.synchronize()
+    # device time of the level loop: max over ranks of the CUDA-event total
+    t = torch.tensor([sum(gpu_ms)], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_total_ms = float(t.item())
+    lt = torch.tensor([launches], dtype=torch.int64, device=eng.device)
+    dist.all_reduce(lt)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        parity = check_result(args.model, res.distinct, res.generated, res.depth, res.levels, res.deadlocks)
+        steps = args.steps
+        N, G = res.distinct, res.generated
+        W = eng.ck.words
+        value = steps * N / (gpu_total_ms / 1000.0)
+        e2e = steps * N / sum(secs)
+        peak, peak_src = measured_peaks()
+        ins_bytes = (G * 32 + N * 8) / world
+        ach = steps * ins_bytes / (ins_ms / 1000.0) / 1e9 if ins_ms else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "states/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": gpu_total_ms / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic (the .cfg is the input; no RNG)",
+            "config": config_for(args.model, {"distinct": N, "generated": G, "depth": res.depth, "state_words": W,
+                                              "parity": parity, "parallelism": f"fingerprint-sharded x{world}",
+                                              "per_rank_distinct": res.per_rank_distinct,
+                                              "exchanged_rows_per_step": res.exchanged_rows}),
+            "roofline": {"kernel": "k_insert (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "avg_launch_ms": ins_ms / max(1, n_ins), "launches": n_ins},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e, "unit": "states/s", "ms_per_step": 1000.0 * sum(secs) / steps,
+                    "h2d_bytes_per_step": (res.depth + 1) * 64 * world, "d2h_bytes_per_step": (res.depth + 1) * 81 * 8 * world},
+            "gpu_launches": int(lt.item()),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=DEFAULT_MODEL)
+    ap.add_argument("--table-log2", type=int, default=0)
+    ap.add_argument("--max-states", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    g = golden_for(args.model)
+    if g and not args.max_states:
+        args.max_states = int(g["distinct"] * 1.02) + 1024
+    if g and not args.table_log2:
+        per_rank = g["distinct"] / max(1, int(os.environ.get("WORLD_SIZE", "1")))
+        lg = 20
+        while (1 << lg) < 2.2 * per_rank:
+            lg += 1
+        args.table_log2 = lg
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        if args.max_states and g:
+            args.max_states = int(g["distinct"] / world * 1.25) + 4096
+        return run_sharded(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,269 @@
+"""Fingerprint-sharded BFS across ranks: one process per GPU, ``torch.distributed`` for the plumbing.
+
+This is the multi-GPU form of the hot path (TLC's analogue is the
+fingerprint-partitioned FPSet of ``tlc2.tool.distributed``).  Every rank owns the slice of the
+fingerprint space ``owner = (fp >> 32) * world >> 32`` -- its own hash set, state store and
+frontier.  Per BFS level and per frontier chunk:
+
+  1. K1 expands the local frontier chunk and buckets each successor row by owner rank
+     (``kmc_shard_expand``; the bucketing happens inside the expand kernel);
+  2. ranks exchange per-destination row counts (all_gather) and then the rows themselves
+     (all-to-all-v as one batch of isend/irecv -- NCCL over NVLink on GPUs, gloo in the CPU tests);
+  3. K2 inserts what a rank received into its own set and appends new states to its own store
+     (``kmc_shard_insert``).
+
+A level ends with an all-reduce of (new states, violation flag); the search ends when no rank
+found a new state.  Distinct = sum of per-rank set sizes, depth = number of levels: both are
+independent of the partition, hence bit-exact across 1/2/4/8 ranks.
+
+The class is written against a small engine interface (``ShardEngine``) so that the same driver
+code runs over the CUDA engine (``CudaShardEngine``, via the C ABI) and, in the CPU-only tests,
+over a host stand-in built from the test harness.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+from .runtime import Checker, ShardBuffers
+
+
+class ShardEngine:
+    """What the driver needs from one rank's engine."""
+    world: int
+    rank: int
+    row_words: int
+    chunk_states: int
+    device: torch.device
+
+    def begin(self): ...
+    def seed_init(self): ...
+    def expand(self, first: int, count: int): ...
+    def counts(self) -> list[int]: ...                     # rows produced for each owner (syncs)
+    def send_view(self, dest: int, rows: int) -> torch.Tensor: ...   # int64 [rows * row_words]
+    def reserve_recv(self, rows: int): ...                 # called once per round before recv_view
+    def recv_view(self, offset_rows: int, rows: int) -> torch.Tensor: ...
+    def insert_received(self, rows: int): ...              # rows contiguous at the start of recv
+    def insert_local(self, rows: int): ...                 # world == 1 fast path: rows in region 0
+    def reset_cand(self): ...
+    def level_done(self) -> tuple[int, int]: ...           # (first, count) of the new level
+    def finish(self): ...
+    def stats(self) -> dict: ...
+    def violation(self): ...
+
+
+class _DevArray:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+class CudaShardEngine(ShardEngine):
+    """One rank of the CUDA engine, driven through the kmc_shard_* entry points."""
+
+    def __init__(self, model: str, rank: int, world: int, device: int, **options):
+        self.ck = Checker(model, device=device, rank=rank, world=world, **options)
+        self.rank, self.world = rank, world
+        self.device = torch.device("cuda", device)
+        self.lib = self.ck.lib
+        b = ShardBuffers()
+        self.ck._check(self.lib.kmc_shard_buffers(self.ck.ctx, ctypes.byref(b)))
+        self.row_words = b.row_words
+        self.region_rows = b.region_rows
+        self.recv_rows_cap = b.recv_rows_cap
+        self.chunk_states = max(1, self.region_rows // self.ck.info.max_fanout)
+        n_cand = self.region_rows * world * self.row_words
+        self.cand = torch.as_tensor(_DevArray(b.cand, n_cand), device=self.device)
+        self.recv = (torch.as_tensor(_DevArray(b.recv, self.recv_rows_cap * self.row_words), device=self.device)
+                     if world > 1 else self.cand)
+        self._recv_ptr = b.recv if world > 1 else b.cand
+        self._cand_ptr = b.cand
+
+    def begin(self):
+        self.ck._check(self.lib.kmc_shard_begin(self.ck.ctx))
+
+    def seed_init(self):
+        self.ck._check(self.lib.kmc_shard_seed_init(self.ck.ctx))
+
+    def expand(self, first, count):
+        self.ck._check(self.lib.kmc_shard_expand(self.ck.ctx, first, count))
+
+    def counts(self):
+        buf = (ctypes.c_uint64 * 8)()
+        self.ck._check(self.lib.kmc_shard_counts(self.ck.ctx, buf))
+        return [int(buf[d]) for d in range(self.world)]
+
+    def send_view(self, dest, rows):
+        off = dest * self.region_rows * self.row_words
+        return self.cand[off: off + rows * self.row_words]
+
+    def reserve_recv(self, rows):
+        if rows > self.recv_rows_cap:
+            raise RuntimeError(f"rank {self.rank}: {rows} incoming rows exceed the receive buffer "
+                               f"({self.recv_rows_cap} rows); raise cand_bytes")
+
+    def recv_view(self, offset_rows, rows):
+        return self.recv[offset_rows * self.row_words: (offset_rows + rows) * self.row_words]
+
+    def insert_received(self, rows):
+        self.ck._check(self.lib.kmc_shard_insert(self.ck.ctx, self._recv_ptr, rows, None))
+
+    def insert_local(self, rows):
+        self.ck._check(self.lib.kmc_shard_insert(self.ck.ctx, self._cand_ptr, rows, None))
+
+    def reset_cand(self):
+        self.ck._check(self.lib.kmc_shard_reset_cand(self.ck.ctx))
+
+    def level_done(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self.ck._check(self.lib.kmc_shard_level_done(self.ck.ctx, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
+    def finish(self):
+        self.ck._check(self.lib.kmc_shard_sync(self.ck.ctx))
+
+    def stats(self):
+        return self.ck.stats()
+
+    def violation(self):
+        return self.ck.violation()
+
+    def trace(self):
+        return self.ck.trace()
+
+    def close(self):
+        self.ck.close()
+
+
+@dataclass
+class ShardedResult:
+    distinct: int
+    generated: int
+    depth: int
+    deadlocks: int
+    levels: list[int]
+    complete: bool
+    violation: dict | None
+    per_rank_distinct: list[int]
+    seconds: float
+    exchanged_rows: int
+    stats: dict = field(default_factory=dict)
+
+
+class ShardedChecker:
+    """Collective driver: every rank constructs one and calls ``run()`` together."""
+
+    def __init__(self, engine: ShardEngine, group=None, cont: bool = False):
+        self.e = engine
+        self.group = group
+        self.cont = cont
+        self.world, self.rank = engine.world, engine.rank
+
+    # -- collectives -----------------------------------------------------------
+    def _all_gather_counts(self, counts: list[int]) -> list[list[int]]:
+        if self.world == 1:
+            return [counts]
+        t = torch.tensor(counts, dtype=torch.int64, device=self.e.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return [o.tolist() for o in out]
+
+    def _all_reduce(self, vals: list[int], op=dist.ReduceOp.SUM) -> list[int]:
+        if self.world == 1:
+            return vals
+        t = torch.tensor(vals, dtype=torch.int64, device=self.e.device)
+        dist.all_reduce(t, op=op, group=self.group)
+        return t.tolist()
+
+    def _exchange(self, counts: list[int]) -> int:
+        """all-to-all-v of candidate rows; returns the number of rows now in the recv buffer."""
+        matrix = self._all_gather_counts(counts)           # matrix[src][dst]
+        incoming = [matrix[src][self.rank] for src in range(self.world)]
+        self.e.reserve_recv(sum(incoming))
+        ops, off = [], 0
+        for src in range(self.world):
+            n = incoming[src]
+            if n:
+                view = self.e.recv_view(off, n)
+                if src == self.rank:
+                    view.copy_(self.e.send_view(self.rank, n))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, view, src, group=self.group))
+            off += n
+        for dst in range(self.world):
+            n = counts[dst]
+            if n and dst != self.rank:
+                ops.append(dist.P2POp(dist.isend, self.e.send_view(dst, n), dst, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.e.device.type == "cuda":
+            torch.cuda.current_stream(self.e.device).synchronize()
+        self.exchanged += sum(counts) - counts[self.rank]
+        return off
+
+    def _round(self, first: int, count: int, init: bool = False):
+        """One expand -> exchange -> insert round on a frontier chunk (count may be 0 on idle ranks)."""
+        e = self.e
+        if not init:
+            e.reset_cand()
+            if count:
+                e.expand(first, count)
+        counts = e.counts()
+        if self.world == 1:
+            if counts[0]:
+                e.insert_local(counts[0])
+            return
+        rows = self._exchange(counts)
+        if rows:
+            e.insert_received(rows)
+
+    # -- the search ------------------------------------------------------------
+    def run(self) -> ShardedResult:
+        e = self.e
+        self.exchanged = 0
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        t0 = time.perf_counter()
+        e.begin()
+        e.seed_init()
+        self._round(0, 0, init=True)
+        first, count = e.level_done()
+        levels: list[int] = []
+        complete, stopped = True, False
+        while True:
+            total, viol = self._all_reduce([count, 1 if e.violation() else 0])
+            if viol and not self.cont:
+                stopped = True
+                if total:
+                    complete = False
+                break
+            if total == 0:
+                break
+            levels.append(total)
+            my_chunks = (count + e.chunk_states - 1) // e.chunk_states
+            n_chunks = self._all_reduce([my_chunks], op=dist.ReduceOp.MAX)[0] if self.world > 1 else my_chunks
+            for c in range(n_chunks):
+                off = c * e.chunk_states
+                n = max(0, min(e.chunk_states, count - off))
+                self._round(first + off, n)
+            first, count = e.level_done()
+        e.finish()
+        st = e.stats()
+        sums = self._all_reduce([st["distinct"], st["generated"], st["deadlocks"]])
+        per_rank = self._all_gather_counts([st["distinct"]])
+        seconds = time.perf_counter() - t0
+        if self.world > 1:
+            seconds = self._all_reduce_max_float(seconds)
+        return ShardedResult(distinct=sums[0], generated=sums[1], depth=len(levels), deadlocks=sums[2], levels=levels,
+                             complete=complete and not stopped,
+                             violation=e.violation(), per_rank_distinct=[p[0] for p in per_rank], seconds=seconds,
+                             exchanged_rows=self.exchanged, stats=st)
+
+    def _all_reduce_max_float(self, x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=self.e.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())

@@ -54,11 +54,13 @@ def main():
     for name, spec in reg.items():
         if only and name not in only:
             continue
+        if spec.get("large") and name not in only:
+            continue                    # minutes of CPU and tens of GB: only when asked for by name
         cfg_text = open(os.path.join(ROOT, spec["cfg"])).read()
         cfg = parse_cfg(cfg_text)
         model, params = spec["kso"]
         t0 = time.time()
-        b = kso.run(model, params, max_states=4_000_000, invariants=cfg.invariants)
+        b = kso.run(model, params, max_states=spec.get("max_states", 4_000_000), invariants=cfg.invariants)
         g = {"module": spec["module"], "cfg": spec["cfg"], "kso": spec["kso"],
              "distinct": b["distinct"], "generated": b["generated"], "depth": b["depth"], "levels": b["levels"],
              "deadlocks": b["deadlocks"], "first_violation_level": b["first_violation_level"],
