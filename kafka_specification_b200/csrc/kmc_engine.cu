@@ -139,6 +139,7 @@ __device__ __noinline__ void record_violation(const Params& p, const State& s, u
 // ----------------------------------------------------------------------------------------
 // K1: expand
 // ----------------------------------------------------------------------------------------
+template <bool MULTI>
 struct CandSink {
   const Params& p;
   uint64_t parent_ref;
@@ -148,11 +149,11 @@ struct CandSink {
   __device__ __forceinline__ void emit(const State& s, int action) {
     ++n;
     uint32_t dest = 0;
-    if (p.world > 1) dest = owner_of(fingerprint(s), p.world);
+    if (MULTI) dest = owner_of(fingerprint(s), p.world);
     // warp-aggregated slot claim: lanes that reached this emit site together and target the
     // same owner share one atomic
     unsigned active = __activemask();
-    unsigned peers = (p.world > 1) ? __match_any_sync(active, dest) : active;
+    unsigned peers = MULTI ? __match_any_sync(active, dest) : active;
     unsigned lane = lane_id();
     int leader = __ffs(peers) - 1;
     unsigned long long base = 0;
@@ -172,24 +173,67 @@ struct CandSink {
   __device__ __forceinline__ void fail(int code) { failed = code; }
 };
 
-__global__ void __launch_bounds__(128) k_expand(Params p, uint64_t first, uint64_t count) {
+// The lowered Next is hundreds of KB of straight-line SASS -- far beyond the SM's instruction
+// caches.  expand() is therefore cut (by the lowering) into NUM_GROUPS groups of ~1k instructions,
+// and the whole CTA sweeps ONE group at a time over a tile of EXPAND_BLOCK x spt states
+// (__syncthreads between groups keeps all 16 warps of the SM in the same group), so every fetched
+// instruction line serves 16 warps x spt states instead of one warp once.
+static constexpr int EXPAND_BLOCK = 512;
+static constexpr int EXPAND_SPT = 4;
+
+__device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
+#pragma unroll
+  for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
+}
+
+template <int G, bool MULTI>
+struct GroupRunner {
+  static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
+                                              int spt, unsigned* nsucc, int& failed) {
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < spt; ++j) {
+      uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
+      if (i < count) {
+        State s;
+        load_state(s, p.store + (first + i) * W);
+        CandSink<MULTI> sink{p, (first + i) | ((uint64_t)p.rank << 40), 0, 0};
+        M::expand_group(M::GroupTag<G>{}, s, sink);
+        nsucc[j] += (unsigned)sink.n;
+        failed |= sink.failed;
+      }
+    }
+    GroupRunner<G + 1, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed);
+  }
+};
+template <bool MULTI>
+struct GroupRunner<M::NUM_GROUPS, MULTI> {
+  static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&) {}
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t first, uint64_t count, int spt) {
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    State s;
-    const uint64_t* src = p.store + (first + i) * W;
-#pragma unroll
-    for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
-    CandSink sink{p, (first + i) | ((uint64_t)p.rank << 40), 0, 0};
-    M::expand(s, sink);
-    gen += sink.n;
-    if ((unsigned)sink.n > maxfan) maxfan = sink.n;
-    if (sink.failed) failed = sink.failed;
-    if (sink.n == 0) {
-      ++dead;
-      if (p.check_deadlock) record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+  const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
+  for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
+    unsigned nsucc[EXPAND_SPT] = {0, 0, 0, 0};
+    GroupRunner<0, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed);
+#pragma unroll 1
+    for (int j = 0; j < spt; ++j) {
+      uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
+      if (i >= count) continue;
+      gen += nsucc[j];
+      if (nsucc[j] > maxfan) maxfan = nsucc[j];
+      if (nsucc[j] == 0) {
+        ++dead;
+        if (p.check_deadlock) {
+          State s;
+          load_state(s, p.store + (first + i) * W);
+          record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+        }
+      }
     }
   }
   // warp reduce the statistics, one atomic per warp
@@ -606,8 +650,14 @@ static int launch_insert(Engine& E, const uint64_t* rows, const unsigned long lo
 
 static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
   Params p = E.params();
+  // small levels: fewer states per thread so that every SM still gets a tile
+  int spt = EXPAND_SPT;
+  while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
+  uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
+  int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
   TimedLaunch t(E, 0);
-  k_expand<<<grid_for(E, count, 128, 8), 128, 0, E.stream>>>(p, first, count);
+  if (E.world > 1) k_expand<true><<<grid, EXPAND_BLOCK, 0, E.stream>>>(p, first, count, spt);
+  else k_expand<false><<<grid, EXPAND_BLOCK, 0, E.stream>>>(p, first, count, spt);
   CK(cudaGetLastError());
   return KMC_OK;
 }

@@ -44,11 +44,11 @@ class Marker:
 
 
 class Thunk:
-    __slots__ = ("expr", "ctx", "fm", "env", "val", "block", "done")
+    __slots__ = ("expr", "ctx", "fm", "env", "val", "block", "done", "unit")
 
     def __init__(self, expr, ctx, fm, env):
         self.expr, self.ctx, self.fm, self.env = expr, ctx, fm, env
-        self.val, self.block, self.done = None, None, False
+        self.val, self.block, self.done, self.unit = None, None, False, -1
 
 
 class Closure:
@@ -59,28 +59,41 @@ class Closure:
 
 
 class CG:
-    """Structured C emitter with block-scoped temporaries."""
+    """Structured C emitter with block-scoped temporaries.
 
-    def __init__(self):
+    ``root`` is the block id of the function body; a fresh CG continuing the same function
+    prologue (``fork``) keeps the root id and the prologue's CSE table, so that values computed in
+    the prologue stay valid in every group function that replicates it."""
+    _ids = itertools.count(1)
+
+    def __init__(self, root: int | None = None, cse: dict | None = None, next_tmp: int = 0):
         self.lines: list[str] = []
         self.depth = 1
-        self.blocks = [0]
-        self.next_block = 1
-        self.next_tmp = 0
-        self.cse: dict[tuple[str, str], tuple[str, int]] = {}
+        self.root = next(CG._ids) if root is None else root
+        self.blocks = [self.root]
+        self.conds: list[str | None] = [None]
+        self.next_tmp = next_tmp
+        self.cse: dict[tuple[str, str], tuple[str, int]] = dict(cse or {})
+
+    def fork(self) -> "CG":
+        return CG(self.root, {k: v for k, v in self.cse.items() if v[1] == self.root}, self.next_tmp)
+
+    def pristine(self) -> bool:
+        return not self.lines and self.depth == 1
 
     def emit(self, s: str):
         self.lines.append("  " * self.depth + s)
 
-    def open(self, head: str = ""):
+    def open(self, head: str = "", cond: str | None = None):
         self.emit(head + " {" if head else "{")
         self.depth += 1
-        self.blocks.append(self.next_block)
-        self.next_block += 1
+        self.blocks.append(next(CG._ids))
+        self.conds.append(cond)
 
     def close(self):
         self.depth -= 1
         self.blocks.pop()
+        self.conds.pop()
         self.emit("}")
 
     def tmp(self, ctype: str, expr: str) -> str:
@@ -95,6 +108,8 @@ class CG:
         return name
 
     def mark(self):
+        if self.depth != len(self.blocks):
+            raise LowerError("internal: unbalanced blocks")
         return (len(self.lines), self.next_tmp, dict(self.cse))
 
     def rollback(self, m):
@@ -126,6 +141,11 @@ class Lowerer:
         self.layout: L.Layout | None = None
         self.actions: list[dict] = []         # {"name", "module", "line", "col", ...}
         self.emit_sites = 0
+        self.units: list[tuple[list[str], int]] = []   # (lines, emit sites) of independently compilable pieces
+        self.unit_id = 0
+        self._unit_emit_mark = 0
+        self.prologue: list[str] = []
+        self.enc_cache: dict[int, tuple] = {}          # id(sval) -> (type, sval, code expr) for values decoded from a code
 
     # ------------------------------------------------------------------ atoms
     def _intern_cfg_atoms(self):
@@ -569,10 +589,10 @@ class Lowerer:
 
     # ------------------------------------------------------------ evaluation
     def force(self, t: Thunk):
-        if t.done and (t.block in self.cg.blocks or is_static(t.val)):
+        if t.done and (is_static(t.val) or (t.block in self.cg.blocks and (t.unit == self.unit_id or t.block == self.cg.root and t.unit == -2))):
             return t.val
         v = self.ev(t.expr, t.ctx, t.fm, t.env)
-        t.val, t.block, t.done = v, self.cg.blocks[-1], True
+        t.val, t.block, t.done, t.unit = v, self.cg.blocks[-1], True, self.unit_id
         if self._spec_thunks is not None:
             self._spec_thunks.append(t)
         return v
@@ -1066,7 +1086,7 @@ class Lowerer:
                     break
         return guards
 
-    def exists_each(self, bounds, body, ctx, fm, env, S, k):
+    def exists_each(self, bounds, body, ctx, fm, env, S, k, split=False):
         """Calls k(guard, env2) for every binding of ``\\E bounds : body`` (pinned or enumerated)."""
         markers = []
         env2 = dict(env)
@@ -1090,9 +1110,14 @@ class Lowerer:
                 else:
                     m = rest[0]
                     for g, x in self.distinct_items(m.domain):
+                        # in action context an unconditional binding reached before any code was
+                        # emitted is a point where expand() can be cut into separate functions
+                        cut = split and g is True and self.b_and(g_all) is True and self.cg.pristine()
                         m.value, m.bound = x, True
                         rec(g_all + [g])
                         m.bound, m.value = False, None
+                        if cut:
+                            self.end_unit()
             for m in newly:
                 m.bound, m.value = False, None
 
@@ -1121,16 +1146,24 @@ class Lowerer:
             self.gen_next([(x, ctx, fm, env) for x in e[1]] + rest, st1, label)
             return
         if k == "or":
+            split = self.cg.pristine()
             for x in e[1]:
-                self.cg.open()
-                self.gen_next([(x, ctx, fm, env)] + rest, st1, label)
-                self.cg.close()
+                if split:
+                    self.gen_next([(x, ctx, fm, env)] + rest, st1, label)
+                    self.end_unit()
+                else:
+                    self.cg.open()
+                    self.gen_next([(x, ctx, fm, env)] + rest, st1, label)
+                    self.cg.close()
             return
         if k == "quant" and e[1] == "E":
             def kont(guard, env2):
                 env3 = {n: (v.value if isinstance(v, Marker) else v) for n, v in env2.items()}
+                split = guard is True and self.cg.pristine()
                 self.guarded(guard, lambda: self.gen_next([(e[3], ctx, fm, env3)] + rest, st1, label))
-            self.exists_each(e[2], e[3], ctx, fm, env, self.cur, kont)
+                if split:
+                    self.end_unit()
+            self.exists_each(e[2], e[3], ctx, fm, env, self.cur, kont, split=True)
             return
         if k == "let":
             self.gen_next([(e[2], ctx, fm, self.let_env(e[1], ctx, fm, env))] + rest, st1, label)
@@ -1182,9 +1215,22 @@ class Lowerer:
         if cond is True:
             body()
             return
-        self.cg.open(f"if ({cond.s})")
+        if cond.s in self.cg.conds:
+            body()
+            return
+        self.cg.open(f"if ({cond.s})", cond.s)
         body()
         self.cg.close()
+
+    def end_unit(self):
+        """Close the current independently-compilable piece of expand() and start a new one."""
+        if self.cg.depth != 1:
+            raise LowerError("internal: end_unit inside an open block")
+        if self.cg.lines:
+            self.units.append((self.cg.lines, self.emit_sites - self._unit_emit_mark))
+        self._unit_emit_mark = self.emit_sites
+        self.unit_id += 1
+        self.cg = self._unit_base.fork()
 
     def action_id(self, d: Def) -> int:
         for i, a in enumerate(self.actions):
@@ -1251,10 +1297,20 @@ class Lowerer:
         return r.defn, r.ctx
 
     def begin_function(self):
-        """Fresh emitter + symbolic reads of every state atom."""
+        """Fresh emitter + symbolic reads of every state atom.  Whatever the reads emit (decode
+        temporaries) becomes the function prologue, replicated in every group function."""
         self.cg = CG()
         self.read_cache = {}
+        self.enc_cache = {}
+        self.unit_id = -2                      # values forced while reading belong to the prologue
         self.cur = {v: self.read_ty(self.layout.var_types[v]) for v in self.variables}
+        self.prologue = self.cg.lines
+        self.cg.lines = []
+        self._unit_base = self.cg
+        self.units = []
+        self.unit_id = 0
+        self._unit_emit_mark = self.emit_sites
+        self.cg = self._unit_base.fork()
 
     def unpack_lines(self) -> list[str]:
         out = []

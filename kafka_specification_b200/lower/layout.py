@@ -614,7 +614,9 @@ class TSet(Ty):
         items = []
         for i, a in enumerate(self.slots):
             g = SBool(f"({i} < (int)a{self.count_atom.index})")
-            items.append((g, self.elem.dec(lw, f"a{a.index}")))
+            x = self.elem.dec(lw, f"a{a.index}")
+            lw.enc_cache[id(x)] = (self.elem, x, f"(int)a{a.index}")     # re-encoding x is the identity
+            items.append((g, x))
         return SSet(items)
 
     def write(self, lw, v, out):
@@ -637,7 +639,13 @@ class TSet(Ty):
             return
         # canonical sorted array: dedup, rank, scatter  (O(m^2) compares, m = #candidate elements)
         items = self._items(lw, v)
-        cs = [lw.tmp_int(self.elem.enc(lw, x)) for _, x in items]
+        cs = []
+        for _, x in items:
+            hit = lw.enc_cache.get(id(x))
+            if hit is not None and hit[0] is self.elem and hit[1] is x:
+                cs.append(hit[2])
+            else:
+                cs.append(lw.tmp_int(self.elem.enc(lw, x)))
         ps: list[str] = []
         for i, (g, _) in enumerate(items):
             terms = [lw.bstr(g)] + [f"!({ps[j]} && {cs[j]} == {cs[i]})" for j in range(i)]

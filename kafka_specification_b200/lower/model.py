@@ -21,7 +21,7 @@ from . import layout as L
 from .compiler import Closure, Lowerer, Marker, Thunk
 from .svals import LowerError, SLazy, is_atom_const, is_const, is_int_const
 
-LOWERING_VERSION = 1
+LOWERING_VERSION = 2
 
 
 @dataclass
@@ -348,7 +348,8 @@ struct State {{ uint64_t w[W]; }};
 """
 
 
-def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | None = None) -> LoweredModel:
+def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | None = None,
+                group_lines: int = 160) -> LoweredModel:
     cfg = parse_cfg(cfg_text)
     root = load_root(module, search_dirs)
     lw = Lowerer(root, cfg)
@@ -398,11 +399,26 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     else:
         start = [(next_e, root, None, {})]
     lw.gen_next(start, {}, None)
-    expand_lines = lw.cg.lines
+    lw.end_unit()
+    expand_prologue = list(lw.prologue)
+    # pack consecutive units into groups of bounded size: each group becomes one function that the
+    # CUDA engine sweeps over a tile of states, so that its code stays resident in the SM's
+    # instruction cache (a fully unrolled Next is hundreds of KB of SASS)
+    groups: list[list[str]] = []
+    cur_lines: list[str] = []
+    for lines, _ in lw.units:
+        if cur_lines and len(cur_lines) + len(lines) > group_lines:
+            groups.append(cur_lines)
+            cur_lines = []
+        cur_lines = cur_lines + ["  {"] + ["  " + l for l in lines] + ["  }"]
+    if cur_lines or not groups:
+        groups.append(cur_lines)
+    expand_lines = [l for g in groups for l in g]
     max_fanout = lw.emit_sites
 
     # invariants
     lw.begin_function()
+    inv_prologue = list(lw.prologue)
     inv_lines_start = len(lw.cg.lines)
     for i, inv in enumerate(cfg.invariants):
         idf, ictx = lw.named_def(inv)
@@ -411,7 +427,7 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
             lw.cg.emit(f"return {i};")
         elif c is not True:
             lw.cg.emit(f"if (!({c.s})) return {i};")
-    inv_lines = lw.cg.lines[inv_lines_start:]
+    inv_lines = inv_prologue + lw.cg.lines[inv_lines_start:]
 
     # constraints
     lw.begin_function()
@@ -420,7 +436,7 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
         cdf, cctx = lw.named_def(con)
         conds.append(lw.ev_bool(cdf.body, cctx, cdf.module, {}))
     c_all = lw.b_and(conds)
-    con_lines = list(lw.cg.lines)
+    con_lines = list(lw.prologue) + list(lw.cg.lines)
     con_lines.append(f"  return {lw.bstr(c_all)};")
 
     name = name or module
@@ -436,10 +452,20 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     for wds in init_words:
         parts.append("  {" + ", ".join(f"0x{w:x}ull" for w in wds) + "},")
     parts.append("};")
-    parts.append("/* successor enumeration: sink.emit(const State&, int action) per successor; sink.fail(code) on a layout trap */")
+    parts.append("/* successor enumeration: sink.emit(const State&, int action) per successor; sink.fail(code) on a layout trap.")
+    parts.append("   expand() = the groups in order; a group is a slice of the Next disjuncts/bindings small enough to stay")
+    parts.append("   in the instruction cache while the engine sweeps it over a tile of states. */")
+    parts.append(f"static constexpr int NUM_GROUPS = {len(groups)};")
+    parts.append("template <int G> struct GroupTag {};")
+    for gi, glines in enumerate(groups):
+        parts.append(f"template <class Sink> KMC_HD void expand_group(GroupTag<{gi}>, const State& s, Sink& sink) {{")
+        parts.extend(unpack)
+        parts.extend(expand_prologue)
+        parts.extend(glines)
+        parts.append("}")
     parts.append("template <class Sink> KMC_HD void expand(const State& s, Sink& sink) {")
-    parts.extend(unpack)
-    parts.extend(expand_lines)
+    for gi in range(len(groups)):
+        parts.append(f"  expand_group(GroupTag<{gi}>{{}}, s, sink);")
     parts.append("}")
     parts.append("/* index of the first violated INVARIANT of the cfg, or -1 */")
     parts.append("KMC_HD int first_violated_invariant(const State& s) {")

@@ -340,9 +340,15 @@ class Checker:
         return out
 
     def run(self, raise_on_error: bool = True) -> RunResult:
-        rc = self.lib.kmc_run(self.ctx)
-        if rc != 0 and raise_on_error:
-            self._check(rc)
+        self.last_rc = self.lib.kmc_run(self.ctx)
+        if self.last_rc != 0 and raise_on_error:
+            self._check(self.last_rc)
+        return self.result()
+
+    def error_text(self, rc: int) -> str:
+        return self.lib.kmc_strerror(self.ctx, rc).decode()
+
+    def result(self) -> RunResult:
         st = self.stats()
         viol = self.violation()
         return RunResult(distinct=st["distinct"], generated=st["generated"], depth=st["depth"], queue=st["queue"],

@@ -1,0 +1,170 @@
+"""``tlc2.TLC``-compatible command line on top of the C ABI.
+
+    python -m kafka_specification_b200.tlc2 [-config F.cfg] [-workers N|auto] [-deadlock] [-continue]
+                                             [-fpbits N] [-maxstates N] [-I dir] [-metadir d] [-tool] SPEC
+
+``SPEC`` is a module name or a path to ``SPEC.tla``; modules it EXTENDS / INSTANCEs are resolved
+from the same directory (and ``-I`` directories), like TLC does.  The spec and its ``.cfg`` are
+lowered ahead of time into a CUDA switch table (cached under ``build/models/``), the BFS runs on
+the GPU through ``libkspecmc.so``, and the summary / error trace are printed in TLC's format.
+``-workers`` is accepted for compatibility (the GPU grid replaces TLC's worker threads).
+
+Exit status follows TLC: 0 no error, 12 safety (invariant) violation, 11 deadlock,
+10 assumption failure, 150 spec/config error, 1 runtime failure (no GPU, table full, ...).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import math
+import os
+import re
+import sys
+import time
+
+from . import build as B
+from .frontend.cfg import CfgError
+from .frontend.modules import ModuleError
+from .frontend.tla_lexer import TlaSyntaxError
+from .lower.svals import LowerError
+from .runtime import Checker, KmcError
+
+EXIT_OK, EXIT_VIOLATION_ASSUMPTION, EXIT_VIOLATION_DEADLOCK, EXIT_VIOLATION_SAFETY, EXIT_ERROR_SPEC = 0, 10, 11, 12, 150
+
+
+def parse_args(argv):
+    ap = argparse.ArgumentParser(prog="tlc2.TLC", add_help=True, prefix_chars="-")
+    ap.add_argument("-config")
+    ap.add_argument("-workers", default="auto")
+    ap.add_argument("-deadlock", action="store_true", help="do NOT check for deadlock (TLC semantics)")
+    ap.add_argument("-continue", dest="cont", action="store_true")
+    ap.add_argument("-fpbits", type=int, default=0, help="log2 of the fingerprint-set slots")
+    ap.add_argument("-maxstates", type=int, default=0)
+    ap.add_argument("-I", action="append", default=[])
+    ap.add_argument("-metadir")
+    ap.add_argument("-tool", action="store_true")
+    ap.add_argument("-device", type=int, default=0)
+    ap.add_argument("-cleanup", action="store_true")
+    ap.add_argument("-nowarning", action="store_true")
+    ap.add_argument("-fp", type=int, default=0)
+    ap.add_argument("-fpmem", type=float, default=0)
+    ap.add_argument("-checkpoint", type=int, default=0)
+    ap.add_argument("-coverage", type=int, default=0)
+    ap.add_argument("spec")
+    return ap.parse_args(argv)
+
+
+def collision_probability(distinct: int, generated: int) -> float:
+    """TLC's 'calculated (optimistic)' estimate: n * (g - n) / 2^64."""
+    return distinct * max(generated - distinct, 1) / 2.0 ** 64
+
+
+def action_location(a: dict | None) -> str:
+    if a is None:
+        return "<Initial predicate>"
+    if "line" in a and a.get("end_line"):
+        return (f"<{a['name']} line {a['line']}, col {a['col']} to line {a['end_line']}, col {a['end_col']} "
+                f"of module {a['module']}>")
+    return f"<{a['name']} of module {a.get('module', '?')}>"
+
+
+def main(argv=None) -> int:
+    a = parse_args(argv if argv is not None else sys.argv[1:])
+    spec_path = a.spec[:-4] if a.spec.endswith(".tla") else a.spec
+    spec_dir = os.path.dirname(os.path.abspath(spec_path)) if os.path.dirname(spec_path) else os.getcwd()
+    module = os.path.basename(spec_path)
+    cfg_path = a.config or os.path.join(spec_dir, module + ".cfg")
+    if not cfg_path.endswith(".cfg"):
+        cfg_path += ".cfg"
+    t0 = time.time()
+    print("TLC2-compatible front end of kspec-mc (B200-native explicit-state model checker)")
+    print(f"Running breadth-first search Model-Checking on the GPU (-workers {a.workers} accepted, unused).")
+    try:
+        cfg_text = open(cfg_path).read()
+    except OSError as e:
+        print(f"Error: cannot read the configuration file {cfg_path}: {e}")
+        return EXIT_ERROR_SPEC
+    os.environ["KSPEC_TLA_PATH"] = os.pathsep.join([spec_dir] + a.I + [os.environ.get("KSPEC_TLA_PATH", "")]).strip(os.pathsep)
+    name = re.sub(r"[^A-Za-z0-9_]", "_", module).lower() + "_" + hashlib.sha256(cfg_text.encode()).hexdigest()[:10]
+    try:
+        print(f"Parsing file {os.path.join(spec_dir, module + '.tla')}")
+        model = B.lower_to_dir(module, cfg_path, name)
+        for w in model.warnings:
+            if not a.nowarning:
+                print(f"Warning: {w}")
+        print(f"Semantic processing of module {module}")
+        B.build_dispatcher()
+        B.compile_model(name)
+    except (TlaSyntaxError, ModuleError, CfgError) as e:
+        print(f"Error: {e}")
+        return EXIT_ERROR_SPEC
+    except LowerError as e:
+        msg = str(e)
+        print(f"Error: {msg}")
+        return EXIT_VIOLATION_ASSUMPTION if "ASSUME" in msg else EXIT_ERROR_SPEC
+    print(f"Starting... ({time.strftime('%Y-%m-%d %H:%M:%S')})")
+    opts = {"device": a.device}
+    if a.fpbits:
+        opts["table_log2"] = a.fpbits
+    if a.maxstates:
+        opts["max_states"] = a.maxstates
+    if a.cont:
+        opts["cont"] = True
+    if a.deadlock:
+        opts["check_deadlock"] = False
+    try:
+        ck = Checker(name, **opts)
+    except KmcError as e:
+        print(f"Error: {e}")
+        return 1
+    print("Computing initial states...")
+    try:
+        r = ck.run(raise_on_error=False)
+        st = r.stats
+        if ck.last_rc != 0:
+            print(f"Error: {ck.error_text(ck.last_rc)}")
+            return 1
+    except KmcError as e:
+        print(f"Error: {e}")
+        return 1
+    n_init = len(model.init_states)
+    print(f"Finished computing initial states: {n_init} distinct state{'s' if n_init != 1 else ''} generated.")
+    exit_code = EXIT_OK
+    if r.violation:
+        v = r.violation
+        if v["kind"] == "deadlock":
+            print("Error: Deadlock reached.")
+            exit_code = EXIT_VIOLATION_DEADLOCK
+        elif v["level"] == 1:
+            print(f"Error: Invariant {v['invariant']} is violated by the initial state:")
+            exit_code = EXIT_VIOLATION_SAFETY
+        else:
+            print(f"Error: Invariant {v['invariant']} is violated.")
+            exit_code = EXIT_VIOLATION_SAFETY
+        if v["level"] != 1 or v["kind"] == "deadlock":
+            print("Error: The behavior up to this point is:")
+        for i, t in enumerate(r.trace):
+            print(f"State {i + 1}: {action_location(t['action'])}")
+            print(t["text"])
+            print()
+    else:
+        print("Model checking completed. No error has been found.")
+        print("  Estimates of the probability that TLC did not check all reachable states")
+        print("  because two distinct states had the same fingerprint:")
+        if ck.info.exact:
+            print("  calculated (optimistic):  val = 0 (states fit 63 bits: the fingerprint is a bijection)")
+        else:
+            print(f"  calculated (optimistic):  val = {collision_probability(r.distinct, r.generated):.1E}")
+    print(f"{r.generated} states generated, {r.distinct} distinct states found, {r.queue} states left on queue.")
+    if r.complete:
+        print(f"The depth of the complete state graph search is {r.depth}.")
+    dt = time.time() - t0
+    print(f"Finished in {int(dt // 60):02d}min {int(dt % 60):02d}s at ({time.strftime('%Y-%m-%d %H:%M:%S')}); "
+          f"GPU search time {st['gpu_ms_total']:.1f} ms "
+          f"({r.distinct / max(st['gpu_ms_total'], 1e-6) * 1000:.3g} distinct states/s)")
+    ck.close()
+    return exit_code
+
+
+if __name__ == "__main__":
+    sys.exit(main())

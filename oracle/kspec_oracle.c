@@ -826,6 +826,7 @@ typedef struct {
   uint64_t table_mask;
   uint8_t* dead;             /* 1: slot allocated by a loser of an insertion race (hole) */
   unsigned want_inv;
+  uint64_t stop_at;
   /* per level */
   uint64_t lvl_first, lvl_end, level;
   _Atomic uint64_t cursor;
@@ -900,6 +901,7 @@ static void* worker(void* arg) {
   out.n = 0;
   uint64_t gen = 0, dead = 0, oom = 0;
   for (;;) {
+    if (atomic_load_explicit(&b->tail, memory_order_relaxed) > b->stop_at) break;   /* truncated run */
     uint64_t start = atomic_fetch_add(&b->cursor, 256);
     if (start >= b->lvl_end) break;
     uint64_t stop = start + 256 < b->lvl_end ? start + 256 : b->lvl_end;
@@ -960,13 +962,19 @@ int kso_run(int model, const int* params, int threads, uint64_t max_states, unsi
   if (max_states == 0) max_states = 1ull << 26;
   b->store_cap = max_states + max_states / 8 + 1024;
   b->store = malloc(b->store_cap * c->ssize);
-  b->dead = calloc(b->store_cap, 1);
+  b->dead = malloc(b->store_cap);
   uint64_t tcap = 1;
   while (tcap < b->store_cap * 2) tcap <<= 1;
-  b->table = calloc(tcap, sizeof(uint32_t));
+  b->table = malloc(tcap * sizeof(uint32_t));
   b->table_mask = tcap - 1;
   b->want_inv = inv_mask;
+  b->stop_at = max_states;
   if (!b->store || !b->dead || !b->table) return -2;
+  /* allocation and first-touch page faults are outside the timed region (as on the GPU side,
+   * where the set and the store are allocated before the clock starts) */
+  memset((void*)b->table, 0, tcap * sizeof(uint32_t));
+  memset(b->dead, 0, b->store_cap);
+  for (uint64_t off = 0; off < b->store_cap * c->ssize; off += 4096) b->store[off] = 0;
   memset(res, 0, sizeof(*res));
   res->state_size = c->ssize;
   struct timespec t0, t1;
@@ -994,8 +1002,15 @@ int kso_run(int model, const int* params, int threads, uint64_t max_states, unsi
     if (width == 0) break;               /* only holes left: the previous level was the last one */
     if (b->level <= 256) res->levels[b->level - 1] = width;
     atomic_store(&b->cursor, b->lvl_first);
-    for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, worker, b);
-    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    int use = threads;                    /* small levels do not pay for idle threads */
+    if (width < 64ull * (uint64_t)use) use = (int)(width / 64) + 1;
+    if (use > threads) use = threads;
+    if (use == 1) {
+      worker(b);
+    } else {
+      for (int t = 0; t < use; ++t) pthread_create(&th[t], NULL, worker, b);
+      for (int t = 0; t < use; ++t) pthread_join(th[t], NULL);
+    }
     if (atomic_load(&b->overflow)) { complete = 0; break; }
     b->lvl_first = b->lvl_end;
     b->lvl_end = atomic_load(&b->tail);
@@ -1003,8 +1018,11 @@ int kso_run(int model, const int* params, int threads, uint64_t max_states, unsi
     if (atomic_load(&b->tail) - atomic_load(&b->holes) > max_states) { complete = 0; break; }
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
-  res->distinct = atomic_load(&b->tail) - atomic_load(&b->holes);
-  if (!complete && atomic_load(&b->overflow)) res->distinct = 0;
+  {
+    uint64_t tail = atomic_load(&b->tail);
+    if (tail > b->store_cap) tail = b->store_cap;
+    res->distinct = tail - atomic_load(&b->holes);
+  }
   res->generated = atomic_load(&b->generated);
   res->depth = b->level - 1 + (complete ? 0 : 1);
   res->deadlocks = atomic_load(&b->deadlocks);
