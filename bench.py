@@ -193,8 +193,8 @@ def run_single(args):
     sampler.start()
     torch.cuda.synchronize()
     gpu_ms, e2e_ms, launches = [], [], 0
-    exp_ms = ins_ms = 0.0
-    n_exp = n_ins = 0
+    exp_ms = ins_ms = inv_ms = 0.0
+    n_exp = n_ins = n_inv = 0
     res = None
     t_bracket = time.perf_counter()
     for _ in range(args.steps):
@@ -206,8 +206,10 @@ def run_single(args):
         launches += st["launches_expand"] + st["launches_insert"] + st["launches_other"]
         exp_ms += st["gpu_ms_expand"]
         ins_ms += st["gpu_ms_insert"]
+        inv_ms += st["gpu_ms_invariant"]
         n_exp += st["launches_expand"]
         n_ins += st["launches_insert"]
+        n_inv += st["launches_other"]
     torch.cuda.synchronize()
     bracket_ms = 1000.0 * (time.perf_counter() - t_bracket)
     clocks = sampler.stop()
@@ -225,6 +227,7 @@ def run_single(args):
     # reads G candidate rows' buckets (32 B each) and writes N*8 (slot) -- plus N*(S+8) store/parent
     exp_bytes = X * S + G * (S + 8)
     ins_bytes = G * 32 + N * 8
+    inv_bytes = N * (S + 8)
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -241,7 +244,9 @@ def run_single(args):
 
     r_exp = roof("k_expand", exp_bytes, exp_ms, n_exp)
     r_ins = roof("k_insert", ins_bytes, ins_ms, n_ins)
-    dominant, other = (r_exp, r_ins) if exp_ms >= ins_ms else (r_ins, r_exp)
+    r_inv = roof("k_invariants", inv_bytes, inv_ms, n_inv)
+    ranked = sorted([r_exp, r_ins, r_inv], key=lambda r: -r["share_of_gpu_time"])
+    dominant, other = ranked[0], ranked[1:]
     cpu = cpu_sample(args.model) if not args.no_cpu_baseline else None
     info = ck.info
     depth = res.depth

@@ -75,6 +75,7 @@ typedef struct {
   uint64_t table_slots;     /* fingerprint-set capacity in 8-byte slots                   */
   uint64_t max_states;      /* state-store capacity                                       */
   uint64_t complete;        /* 1 if the search ran to an empty queue                      */
+  double gpu_ms_invariant;  /* sum over invariant-kernel launches (counted in launches_other) */
 } kmc_stats_t;
 
 typedef struct {

@@ -139,35 +139,108 @@ __device__ __noinline__ void record_violation(const Params& p, const State& s, u
 // ----------------------------------------------------------------------------------------
 // K1: expand
 // ----------------------------------------------------------------------------------------
+// Successor rows are staged per warp in shared memory and flushed in bulk: one global slot claim
+// per flush (instead of one ~600-cycle atomic round trip per emit site), coalesced row stores,
+// and -- multi-rank -- the owner computation (a fingerprint) done with all 32 lanes busy instead
+// of inside the divergent emit site.
+static constexpr int STAGE_ROWS = 96;      // rows per warp
+static constexpr int STAGE_FLUSH = 48;     // flush once at least this many rows are staged
+
+template <bool MULTI>
+__device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t* words, uint64_t meta, bool valid,
+                                                 int& failed) {
+  // one row per lane (valid lanes only), slot claims aggregated per owner
+  State s;
+#pragma unroll
+  for (int i = 0; i < W; ++i) s.w[i] = words[i];
+  uint32_t dest = 0xFFu;
+  if (valid) dest = MULTI ? owner_of(fingerprint(s), p.world) : 0u;
+  unsigned peers = __match_any_sync(0xffffffffu, dest);
+  unsigned lane = lane_id();
+  int leader = __ffs(peers) - 1;
+  unsigned long long base = 0;
+  if (valid && (int)lane == leader) base = atomicAdd(&p.ctr->cand_count[dest], (unsigned long long)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!valid) return;
+  unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+  if (pos >= p.region_rows) {
+    failed = KMC_FAIL_CAND_FULL;
+    return;
+  }
+  uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + pos) * ROW;
+#pragma unroll
+  for (int i = 0; i < W; ++i) row[i] = s.w[i];
+  row[W] = meta;
+}
+
+// called by all 32 lanes of a warp at a converged point
+template <bool MULTI>
+__device__ __forceinline__ void flush_stage(const Params& p, uint64_t* wbuf, unsigned* wcnt, bool force, int& failed) {
+  __syncwarp();
+  unsigned n = *wcnt;
+  if (n > (unsigned)STAGE_ROWS) n = STAGE_ROWS;
+  if (n == 0 || (!force && n < (unsigned)STAGE_FLUSH)) return;
+  unsigned lane = lane_id();
+  if (!MULTI) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&p.ctr->cand_count[0], (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > p.region_rows) {
+      failed = KMC_FAIL_CAND_FULL;
+    } else {
+      uint64_t* dst = p.cand + base * ROW;
+      for (unsigned k = lane; k < n * ROW; k += 32) dst[k] = wbuf[k];      // coalesced
+    }
+  } else {
+    for (unsigned r0 = 0; r0 < n; r0 += 32) {
+      unsigned r = r0 + lane;
+      bool valid = r < n;
+      const uint64_t* row = wbuf + (valid ? r : 0) * ROW;
+      claim_and_store<true>(p, row, row[W], valid, failed);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *wcnt = 0;
+  __syncwarp();
+}
+
 template <bool MULTI>
 struct CandSink {
   const Params& p;
   uint64_t parent_ref;
+  uint64_t* wbuf;      // this warp's staging rows (shared memory)
+  unsigned* wcnt;      // rows staged by this warp
   int n;
   int failed;
 
   __device__ __forceinline__ void emit(const State& s, int action) {
     ++n;
-    uint32_t dest = 0;
-    if (MULTI) dest = owner_of(fingerprint(s), p.world);
-    // warp-aggregated slot claim: lanes that reached this emit site together and target the
-    // same owner share one atomic
+    const uint64_t meta = parent_ref | ((uint64_t)action << 56);
     unsigned active = __activemask();
-    unsigned peers = MULTI ? __match_any_sync(active, dest) : active;
     unsigned lane = lane_id();
-    int leader = __ffs(peers) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(&p.ctr->cand_count[dest], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
-    if (pos >= p.region_rows) {
-      failed = KMC_FAIL_CAND_FULL;
-      return;
-    }
-    uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + pos) * ROW;
+    int leader = __ffs(active) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(wcnt, (unsigned)__popc(active));      // shared-memory atomic
+    base = __shfl_sync(active, base, leader);
+    unsigned pos = base + __popc(active & ((1u << lane) - 1));
+    if (pos < (unsigned)STAGE_ROWS) {
+      uint64_t* row = wbuf + pos * ROW;
 #pragma unroll
-    for (int i = 0; i < W; ++i) row[i] = s.w[i];
-    row[W] = parent_ref | ((uint64_t)action << 56);
+      for (int i = 0; i < W; ++i) row[i] = s.w[i];
+      row[W] = meta;
+    } else {
+      // staging area full (rare burst): straight to global memory, one claim per lane group
+      uint32_t dest = MULTI ? owner_of(fingerprint(s), p.world) : 0u;
+      unsigned long long gpos = atomicAdd(&p.ctr->cand_count[dest], 1ull);
+      if (gpos >= p.region_rows) {
+        failed = KMC_FAIL_CAND_FULL;
+      } else {
+        uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + gpos) * ROW;
+#pragma unroll
+        for (int i = 0; i < W; ++i) row[i] = s.w[i];
+        row[W] = meta;
+      }
+    }
     if (p.count_actions && action < 64) atomicAdd(&p.ctr->action_counts[action], 1ull);
   }
   __device__ __forceinline__ void fail(int code) { failed = code; }
@@ -189,7 +262,7 @@ __device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
 template <int G, bool MULTI>
 struct GroupRunner {
   static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
-                                              int spt, unsigned* nsucc, int& failed) {
+                                              int spt, unsigned* nsucc, int& failed, uint64_t* wbuf, unsigned* wcnt) {
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < spt; ++j) {
@@ -197,29 +270,38 @@ struct GroupRunner {
       if (i < count) {
         State s;
         load_state(s, p.store + (first + i) * W);
-        CandSink<MULTI> sink{p, (first + i) | ((uint64_t)p.rank << 40), 0, 0};
+        CandSink<MULTI> sink{p, (first + i) | ((uint64_t)p.rank << 40), wbuf, wcnt, 0, 0};
         M::expand_group(M::GroupTag<G>{}, s, sink);
         nsucc[j] += (unsigned)sink.n;
         failed |= sink.failed;
       }
+      flush_stage<MULTI>(p, wbuf, wcnt, false, failed);
     }
-    GroupRunner<G + 1, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed);
+    GroupRunner<G + 1, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
   }
 };
 template <bool MULTI>
 struct GroupRunner<M::NUM_GROUPS, MULTI> {
-  static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&) {}
+  static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&,
+                                              uint64_t*, unsigned*) {}
 };
 
 template <bool MULTI>
 __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t first, uint64_t count, int spt) {
+  extern __shared__ uint64_t stage[];                       // [warps][STAGE_ROWS][ROW] then [warps] counters
+  const int warp = threadIdx.x >> 5;
+  uint64_t* wbuf = stage + (size_t)warp * STAGE_ROWS * ROW;
+  unsigned* wcnt = reinterpret_cast<unsigned*>(stage + (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW) + warp;
+  if (lane_id() == 0) *wcnt = 0;
+  __syncwarp();
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
   const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
   for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
     unsigned nsucc[EXPAND_SPT] = {0, 0, 0, 0};
-    GroupRunner<0, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed);
+    GroupRunner<0, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
+    flush_stage<MULTI>(p, wbuf, wcnt, true, failed);
 #pragma unroll 1
     for (int j = 0; j < spt; ++j) {
       uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
@@ -323,7 +405,9 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
       } else {
         ++oom;
       }
-      if (M::NUM_INVARIANTS > 0 && (is_new || !inmodel)) {
+      // TLC also checks invariants on successors discarded by a CONSTRAINT; they are not stored,
+      // so that (rare) case stays here.  New in-model states are checked by k_invariants (K3).
+      if (M::NUM_INVARIANTS > 0 && M::NUM_CONSTRAINTS > 0 && !inmodel) {
         int inv = M::first_violated_invariant(s);
         if (inv >= 0) record_violation(p, s, meta, fp, (uint64_t)inv);
       }
@@ -358,6 +442,22 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
     if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
     if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
+  }
+}
+
+// K3: invariants on the new states of a level.  They sit compacted in the store, so every lane
+// has work (inside k_insert only the ~1/3 of lanes holding a new state would be active).
+__global__ void __launch_bounds__(256) k_invariants(Params p, uint64_t first, const unsigned long long* end_ptr) {
+  uint64_t end = (uint64_t)*end_ptr;
+  if (end > p.max_states) end = p.max_states;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    State s;
+    const uint64_t* src = p.store + i * W;
+#pragma unroll
+    for (int k = 0; k < W; ++k) s.w[k] = __ldcs(src + k);
+    int inv = M::first_violated_invariant(s);
+    if (inv >= 0) record_violation(p, s, p.parent[i], fingerprint(s), (uint64_t)inv);
   }
 }
 
@@ -648,6 +748,15 @@ static int launch_insert(Engine& E, const uint64_t* rows, const unsigned long lo
   return KMC_OK;
 }
 
+static int launch_invariants(Engine& E, uint64_t first, uint64_t count_bound) {
+  if (M::NUM_INVARIANTS == 0) return KMC_OK;
+  Params p = E.params();
+  TimedLaunch t(E, 2);
+  k_invariants<<<grid_for(E, std::max<uint64_t>(count_bound, 1), 256, 8), 256, 0, E.stream>>>(p, first, &E.ctr->store_tail);
+  CK(cudaGetLastError());
+  return KMC_OK;
+}
+
 static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
   Params p = E.params();
   // small levels: fewer states per thread so that every SM still gets a tile
@@ -655,9 +764,16 @@ static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
   while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
   uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
   int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
+  const size_t smem = (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   TimedLaunch t(E, 0);
-  if (E.world > 1) k_expand<true><<<grid, EXPAND_BLOCK, 0, E.stream>>>(p, first, count, spt);
-  else k_expand<false><<<grid, EXPAND_BLOCK, 0, E.stream>>>(p, first, count, spt);
+  if (E.world > 1) k_expand<true><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
+  else k_expand<false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
   CK(cudaGetLastError());
   return KMC_OK;
 }
@@ -711,14 +827,14 @@ static int build_trace(Engine& E, const DevCounters& h, uint64_t level) {
 }
 
 static void accumulate_timing(Engine& E, kmc_stats_t& st) {
-  st.gpu_ms_expand = st.gpu_ms_insert = 0;
+  st.gpu_ms_expand = st.gpu_ms_insert = st.gpu_ms_invariant = 0;
   st.launches_expand = st.launches_insert = st.launches_other = 0;
   for (const LaunchRec& r : E.launches) {
     float ms = 0;
     cudaEventElapsedTime(&ms, r.a, r.b);
     if (r.kind == 0) { st.gpu_ms_expand += ms; st.launches_expand++; }
     else if (r.kind == 1) { st.gpu_ms_insert += ms; st.launches_insert++; }
-    else st.launches_other += 3;
+    else { st.gpu_ms_invariant += ms; st.launches_other++; }
   }
 }
 
@@ -735,6 +851,7 @@ static int engine_run(Engine& E) {
   if (rc) return rc;
   rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, M::NUM_INIT);
   if (rc) return rc;
+  if ((rc = launch_invariants(E, 0, M::NUM_INIT))) return rc;
   DevCounters h;
   rc = read_counters(E, &h);
   if (rc) return rc;
@@ -753,6 +870,7 @@ static int engine_run(Engine& E) {
       if ((rc = launch_expand(E, off, cnt))) return rc;
       if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)M::MAX_FANOUT))) return rc;
     }
+    if ((rc = launch_invariants(E, level_end, (level_end - level_first) * 2))) return rc;
     if ((rc = read_counters(E, &h))) return rc;
     err = fail_to_error(h.fail);
     {
@@ -1036,7 +1154,9 @@ int kmcm_shard_insert(kmcm_ctx* c, const uint64_t* rows_dev, uint64_t rows, uint
 int kmcm_shard_level_done(kmcm_ctx* c, uint64_t* level_first, uint64_t* level_count) {
   if (!c) return KMC_E_BADARG;
   DevCounters h;
-  int rc = read_counters(E, &h);
+  int rc = launch_invariants(E, E.level_first + E.level_count, std::max<uint64_t>(E.level_count * 2, 1024));
+  if (rc) return rc;
+  rc = read_counters(E, &h);
   if (rc) return rc;
   uint64_t prev_end = E.level_first + E.level_count;
   E.level_first = prev_end;

@@ -25,7 +25,7 @@ def main():
             out = {"model": name, "distinct": r.distinct, "generated": r.generated, "depth": r.depth,
                    "deadlocks": r.deadlocks, "complete": r.complete, "violation": r.violation,
                    "gpu_ms": round(r.stats["gpu_ms_total"], 3), "expand_ms": round(r.stats["gpu_ms_expand"], 3),
-                   "insert_ms": round(r.stats["gpu_ms_insert"], 3), "wall_ms": round(r.stats["wall_ms"], 1),
+                   "insert_ms": round(r.stats["gpu_ms_insert"], 3), "invariant_ms": round(r.stats["gpu_ms_invariant"], 3), "wall_ms": round(r.stats["wall_ms"], 1),
                    "probes": r.stats["probes"], "levels": r.levels, "total_s": round(time.time() - t0, 2)}
             print(json.dumps(out), flush=True)
             if r.violation:
