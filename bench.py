@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one complete explicit-state BFS (Init -> empty frontier) of the headline model:
-Kip320 bound to KafkaReplication.tla, 3 brokers, LogSize ("MaxLogLen") 4 (models/Kip320.cfg).
+Kip320 bound to KafkaReplication.tla, 3 brokers, LogSize ("MaxLogLen") 4, MaxRecords 4, MaxLeaderEpoch 3
+(models/Kip320_R4.cfg: 340,433,359 distinct states, depth 42).
 The input is the .cfg; there is no RNG.  The result of every step (distinct, generated, depth,
 per-level widths) is compared with the committed golden before a number is printed.
 
@@ -33,7 +34,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DEFAULT_MODEL = "kip320_3x4_r3e3"
+DEFAULT_MODEL = "kip320_3x4_r4e3"
 METRIC = "distinct states/sec"
 
 

@@ -102,7 +102,9 @@ typedef struct {
 /* model_lib: path of a lowered-model library (libkmc_<model>.so, built ahead of time by
  * `python -m kafka_specification_b200.build`).  options_json: flat JSON object, all keys
  * optional: "device":0, "table_log2":27, "max_states":N, "cand_bytes":N, "rank":0, "world":1,
- * "continue":false, "check_deadlock":true|false (override), "timing":true.             */
+ * "continue":false, "check_deadlock":true|false (override), "timing":true,
+ * "fused":false (single GPU: insert from the expand kernel's staged flush; measured slower),
+ * "stop_after_states":N (bounded run: stop at the first level end holding >= N states).        */
 int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out);
 void kmc_destroy(kmc_ctx* ctx);
 int kmc_model_info(const kmc_ctx* ctx, kmc_model_info_t* out);

@@ -139,6 +139,133 @@ __device__ __noinline__ void record_violation(const Params& p, const State& s, u
 // ----------------------------------------------------------------------------------------
 // K1: expand
 // ----------------------------------------------------------------------------------------
+// ----------------------------------------------------------------------------------------
+// K2 primitives: the fingerprint set
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 ld_bucket_half(const uint64_t* p) {
+  // L2-coherent 128-bit load, no L1 allocation: buckets are touched once per probe
+  ulonglong2 v;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint64_t bucket_of(uint64_t fp, uint64_t bucket_mask) { return (fp ^ (fp >> 31)) & bucket_mask; }
+
+// returns 1 = inserted (new), 0 = already present, -1 = table full.  (lo, hi) = the first bucket,
+// loaded by the caller ahead of time so that several probes are in flight per thread.
+__device__ __forceinline__ int fpset_insert_pre(uint64_t* table, uint64_t bucket_mask, uint64_t fp, ulonglong2 lo,
+                                                 ulonglong2 hi, unsigned& probes) {
+  uint64_t b = bucket_of(fp, bucket_mask);
+  for (int attempt = 0; attempt < 512; ++attempt) {
+    uint64_t* base = table + (b << 2);
+    if (attempt) {
+      lo = ld_bucket_half(base);
+      hi = ld_bucket_half(base + 2);
+    }
+    ++probes;
+    uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+    if (v[0] == fp || v[1] == fp || v[2] == fp || v[3] == fp) return 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v[k] == 0) {
+        unsigned long long old = atomicCAS((unsigned long long*)(base + k), 0ull, (unsigned long long)fp);
+        if (old == 0) return 1;
+        if (old == fp) return 0;
+        // another fingerprint took the slot: keep scanning (slots never empty again)
+      }
+    }
+    b = (b + 1) & bucket_mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int fpset_insert(uint64_t* table, uint64_t bucket_mask, uint64_t fp, unsigned& probes) {
+  const uint64_t* base = table + (bucket_of(fp, bucket_mask) << 2);
+  ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
+  return fpset_insert_pre(table, bucket_mask, fp, lo, hi, probes);
+}
+
+__device__ __forceinline__ int fpset_contains(const uint64_t* table, uint64_t bucket_mask, uint64_t fp) {
+  uint64_t b = bucket_of(fp, bucket_mask);
+  for (int attempt = 0; attempt < 512; ++attempt) {
+    const uint64_t* base = table + (b << 2);
+    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
+    if (lo.x == fp || lo.y == fp || hi.x == fp || hi.y == fp) return 1;
+    if (lo.x == 0 || lo.y == 0 || hi.x == 0 || hi.y == 0) return 0;
+    b = (b + 1) & bucket_mask;
+  }
+  return 0;
+}
+
+// Warp-collective insert of one candidate row per lane (invalid lanes pass valid = false):
+// constraint check, fingerprint, bucket probe + CAS, ballot/popc compaction of the winners into the
+// state store, parent link.  Used by k_insert (rows from HBM) and by the fused flush of k_expand
+// (rows from the warp's shared-memory stage).
+struct Prefetched {
+  uint64_t fp;
+  ulonglong2 lo, hi;
+  bool inmodel;
+};
+
+// first half of an insert: fingerprint + issue the bucket loads (no dependent use yet)
+__device__ __forceinline__ Prefetched prefetch_row(const Params& p, const State& s, bool valid) {
+  Prefetched f;
+  f.fp = 0;
+  f.lo = f.hi = make_ulonglong2(0, 0);
+  f.inmodel = false;
+  if (valid) {
+    f.inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
+    f.fp = fingerprint(s);
+    if (f.inmodel) {
+      const uint64_t* base = p.table + (bucket_of(f.fp, p.bucket_mask) << 2);
+      f.lo = ld_bucket_half(base);
+      f.hi = ld_bucket_half(base + 2);
+    }
+  }
+  return f;
+}
+
+__device__ __forceinline__ void insert_row(const Params& p, const State& s, uint64_t meta, bool valid, const Prefetched& f,
+                                            unsigned& probes, unsigned& oom, int& failed) {
+  bool is_new = false;
+  if (valid) {
+    const bool inmodel = f.inmodel;
+    const uint64_t fp = f.fp;
+    if (inmodel) {
+      int r = fpset_insert_pre(p.table, p.bucket_mask, fp, f.lo, f.hi, probes);
+      if (r < 0) failed = KMC_FAIL_TABLE_FULL;
+      is_new = r > 0;
+    } else {
+      ++oom;
+      // TLC also checks invariants on successors discarded by a CONSTRAINT; they are not stored,
+      // so that (rare) case is handled here.  New in-model states are checked by k_invariants (K3).
+      if (M::NUM_INVARIANTS > 0) {
+        int inv = M::first_violated_invariant(s);
+        if (inv >= 0) record_violation(p, s, meta, fp, (uint64_t)inv);
+      }
+    }
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, is_new);
+  if (mask) {
+    unsigned lane = lane_id();
+    int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(&p.ctr->store_tail, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (is_new) {
+      uint64_t idx = base + __popc(mask & ((1u << lane) - 1));
+      if (idx < p.max_states) {
+        uint64_t* dst = p.store + idx * W;
+#pragma unroll
+        for (int k = 0; k < W; ++k) dst[k] = s.w[k];
+        p.parent[idx] = meta;
+      } else {
+        failed = KMC_FAIL_STORE_FULL;
+      }
+    }
+  }
+}
+
 // Successor rows are staged per warp in shared memory and flushed in bulk: one global slot claim
 // per flush (instead of one ~600-cycle atomic round trip per emit site), coalesced row stores,
 // and -- multi-rank -- the owner computation (a fingerprint) done with all 32 lanes busy instead
@@ -174,14 +301,33 @@ __device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t*
 }
 
 // called by all 32 lanes of a warp at a converged point
-template <bool MULTI>
-__device__ __forceinline__ void flush_stage(const Params& p, uint64_t* wbuf, unsigned* wcnt, bool force, int& failed) {
+struct ExpandStats {
+  unsigned probes, oom;
+};
+
+template <bool MULTI, bool FUSED>
+__device__ __forceinline__ void flush_stage(const Params& p, uint64_t* wbuf, unsigned* wcnt, bool force, int& failed,
+                                             ExpandStats& xs) {
   __syncwarp();
   unsigned n = *wcnt;
   if (n > (unsigned)STAGE_ROWS) n = STAGE_ROWS;
   if (n == 0 || (!force && n < (unsigned)STAGE_FLUSH)) return;
   unsigned lane = lane_id();
-  if (!MULTI) {
+  if (FUSED) {
+    // single GPU: the staged rows never go to HBM -- fingerprint, probe and insert them right
+    // here, 32 at a time with every lane busy.  The probe's DRAM latency overlaps the integer work
+    // of the CTA's other warps.
+    for (unsigned r0 = 0; r0 < n; r0 += 32) {
+      unsigned r = r0 + lane;
+      bool valid = r < n;
+      State s;
+      const uint64_t* row = wbuf + (valid ? r : 0) * ROW;
+#pragma unroll
+      for (int k = 0; k < W; ++k) s.w[k] = row[k];
+      Prefetched f = prefetch_row(p, s, valid);
+      insert_row(p, s, row[W], valid, f, xs.probes, xs.oom, failed);
+    }
+  } else if (!MULTI) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&p.ctr->cand_count[0], (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -251,18 +397,25 @@ struct CandSink {
 // and the whole CTA sweeps ONE group at a time over a tile of EXPAND_BLOCK x spt states
 // (__syncthreads between groups keeps all 16 warps of the SM in the same group), so every fetched
 // instruction line serves 16 warps x spt states instead of one warp once.
-static constexpr int EXPAND_BLOCK = 512;
-static constexpr int EXPAND_SPT = 4;
+#ifndef EXPAND_BLOCK_THREADS
+#define EXPAND_BLOCK_THREADS 1024
+#endif
+static constexpr int EXPAND_BLOCK = EXPAND_BLOCK_THREADS;
+#ifndef EXPAND_SPT_MAX
+#define EXPAND_SPT_MAX 4
+#endif
+static constexpr int EXPAND_SPT = EXPAND_SPT_MAX;
 
 __device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
 #pragma unroll
   for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
 }
 
-template <int G, bool MULTI>
+template <int G, bool MULTI, bool FUSED>
 struct GroupRunner {
   static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
-                                              int spt, unsigned* nsucc, int& failed, uint64_t* wbuf, unsigned* wcnt) {
+                                              int spt, unsigned* nsucc, int& failed, uint64_t* wbuf, unsigned* wcnt,
+                                              ExpandStats& xs) {
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < spt; ++j) {
@@ -275,19 +428,23 @@ struct GroupRunner {
         nsucc[j] += (unsigned)sink.n;
         failed |= sink.failed;
       }
-      flush_stage<MULTI>(p, wbuf, wcnt, false, failed);
+      flush_stage<MULTI, FUSED>(p, wbuf, wcnt, false, failed, xs);
     }
-    GroupRunner<G + 1, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
+    GroupRunner<G + 1, MULTI, FUSED>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt, xs);
   }
 };
-template <bool MULTI>
-struct GroupRunner<M::NUM_GROUPS, MULTI> {
+template <bool MULTI, bool FUSED>
+struct GroupRunner<M::NUM_GROUPS, MULTI, FUSED> {
   static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&,
-                                              uint64_t*, unsigned*) {}
+                                              uint64_t*, unsigned*, ExpandStats&) {}
 };
 
-template <bool MULTI>
-__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t first, uint64_t count, int spt) {
+#ifndef EXPAND_MIN_BLOCKS
+#define EXPAND_MIN_BLOCKS 1
+#endif
+
+template <bool MULTI, bool FUSED>
+__global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_MIN_BLOCKS) k_expand(Params p, uint64_t first, uint64_t count, int spt) {
   extern __shared__ uint64_t stage[];                       // [warps][STAGE_ROWS][ROW] then [warps] counters
   const int warp = threadIdx.x >> 5;
   uint64_t* wbuf = stage + (size_t)warp * STAGE_ROWS * ROW;
@@ -297,11 +454,12 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t f
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
+  ExpandStats xs{0, 0};
   const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
   for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
-    unsigned nsucc[EXPAND_SPT] = {0, 0, 0, 0};
-    GroupRunner<0, MULTI>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
-    flush_stage<MULTI>(p, wbuf, wcnt, true, failed);
+    unsigned nsucc[EXPAND_SPT] = {};
+    GroupRunner<0, MULTI, FUSED>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt, xs);
+    flush_stage<MULTI, FUSED>(p, wbuf, wcnt, true, failed, xs);
 #pragma unroll 1
     for (int j = 0; j < spt; ++j) {
       uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
@@ -324,8 +482,12 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t f
     dead += __shfl_xor_sync(0xffffffffu, dead, o);
     maxfan = max(maxfan, __shfl_xor_sync(0xffffffffu, maxfan, o));
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
+    xs.probes += __shfl_xor_sync(0xffffffffu, xs.probes, o);
+    xs.oom += __shfl_xor_sync(0xffffffffu, xs.oom, o);
   }
   if (lane_id() == 0) {
+    if (xs.probes) atomicAdd(&p.ctr->probes, (unsigned long long)xs.probes);
+    if (xs.oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)xs.oom);
     if (gen) atomicAdd(&p.ctr->generated, gen);
     if (dead) atomicAdd(&p.ctr->deadlocks, dead);
     if (maxfan) atomicMax(&p.ctr->max_fanout_seen, (unsigned long long)maxfan);
@@ -333,105 +495,33 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t f
   }
 }
 
-// ----------------------------------------------------------------------------------------
-// K2: fingerprint-set insert (+ K3 invariants)
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ ulonglong2 ld_bucket_half(const uint64_t* p) {
-  // L2-coherent 128-bit load, no L1 allocation: buckets are touched once per probe
-  ulonglong2 v;
-  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
-  return v;
-}
-
-// returns 1 = inserted (new), 0 = already present, -1 = table full
-__device__ __forceinline__ int fpset_insert(uint64_t* table, uint64_t bucket_mask, uint64_t fp, unsigned& probes) {
-  uint64_t b = (fp ^ (fp >> 31)) & bucket_mask;
-  for (int attempt = 0; attempt < 512; ++attempt) {
-    uint64_t* base = table + (b << 2);
-    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
-    ++probes;
-    uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
-    if (v[0] == fp || v[1] == fp || v[2] == fp || v[3] == fp) return 0;
+__device__ __forceinline__ void load_row(State& s, uint64_t& meta, const uint64_t* rows, uint64_t i, bool valid) {
+  meta = 0;
+  if (valid) {
+    const uint64_t* row = rows + i * ROW;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (v[k] == 0) {
-        unsigned long long old = atomicCAS((unsigned long long*)(base + k), 0ull, (unsigned long long)fp);
-        if (old == 0) return 1;
-        if (old == fp) return 0;
-        // another fingerprint took the slot: keep scanning (slots never empty again)
-      }
-    }
-    b = (b + 1) & bucket_mask;
+    for (int k = 0; k < W; ++k) s.w[k] = __ldcs(row + k);
+    meta = __ldcs(row + W);
   }
-  return -1;
 }
 
-__device__ __forceinline__ int fpset_contains(const uint64_t* table, uint64_t bucket_mask, uint64_t fp) {
-  uint64_t b = (fp ^ (fp >> 31)) & bucket_mask;
-  for (int attempt = 0; attempt < 512; ++attempt) {
-    const uint64_t* base = table + (b << 2);
-    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
-    if (lo.x == fp || lo.y == fp || hi.x == fp || hi.y == fp) return 1;
-    if (lo.x == 0 || lo.y == 0 || hi.x == 0 || hi.y == 0) return 0;
-    b = (b + 1) & bucket_mask;
-  }
-  return 0;
-}
-
+// One candidate row per thread per iteration.  (Two rows per thread -- two sectors in flight per
+// lane -- was measured slower: 72 vs 63 ms on the 340 M-state model; the extra registers cost more
+// occupancy than the added memory-level parallelism gains.)
 __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, const unsigned long long* n_ptr,
                                                  uint64_t n_fixed) {
   const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
   const uint64_t n_round = (n + 31) & ~31ull;
-  unsigned probes = 0;
-  unsigned oom = 0;
+  unsigned probes = 0, oom = 0;
   int failed = 0;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool valid = i < n;
-    State s;
-    uint64_t meta = 0, fp = 0;
-    bool is_new = false, inmodel = false;
-    if (valid) {
-      const uint64_t* row = rows + i * ROW;
-#pragma unroll
-      for (int k = 0; k < W; ++k) s.w[k] = __ldcs(row + k);
-      meta = __ldcs(row + W);
-      inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
-      fp = fingerprint(s);
-      if (inmodel) {
-        int r = fpset_insert(p.table, p.bucket_mask, fp, probes);
-        if (r < 0) failed = KMC_FAIL_TABLE_FULL;
-        is_new = r > 0;
-      } else {
-        ++oom;
-      }
-      // TLC also checks invariants on successors discarded by a CONSTRAINT; they are not stored,
-      // so that (rare) case stays here.  New in-model states are checked by k_invariants (K3).
-      if (M::NUM_INVARIANTS > 0 && M::NUM_CONSTRAINTS > 0 && !inmodel) {
-        int inv = M::first_violated_invariant(s);
-        if (inv >= 0) record_violation(p, s, meta, fp, (uint64_t)inv);
-      }
-    }
-    // compaction of the winners into the state store (next frontier)
-    unsigned mask = __ballot_sync(0xffffffffu, is_new);
-    if (mask) {
-      unsigned lane = lane_id();
-      int leader = __ffs(mask) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(&p.ctr->store_tail, (unsigned long long)__popc(mask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (is_new) {
-        uint64_t idx = base + __popc(mask & ((1u << lane) - 1));
-        if (idx < p.max_states) {
-          uint64_t* dst = p.store + idx * W;
-#pragma unroll
-          for (int k = 0; k < W; ++k) dst[k] = s.w[k];
-          p.parent[idx] = meta;
-        } else {
-          failed = KMC_FAIL_STORE_FULL;
-        }
-      }
-    }
+    const bool v0 = i < n;
+    State s0;
+    uint64_t m0;
+    load_row(s0, m0, rows, i, v0);
+    Prefetched f0 = prefetch_row(p, s0, v0);
+    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
   }
   for (int o = 16; o > 0; o >>= 1) {
     probes += __shfl_xor_sync(0xffffffffu, probes, o);
@@ -497,6 +587,9 @@ struct Engine {
   bool check_deadlock = M::CHECK_DEADLOCK;
   bool timing = true;
   bool count_actions = false;
+  bool fused = false;           // single-GPU kmc_run: insert from the expand kernel's staged flush (measured slower:
+                                // warps waiting on probe latency hold up the CTA-wide group barrier)
+  uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
 
   uint64_t* table = nullptr;
   uint64_t table_slots = 0;
@@ -653,7 +746,7 @@ static int engine_alloc(Engine& E) {
   }
   E.table_slots = 1ull << E.table_log2;
   if (E.max_states == 0) E.max_states = E.table_slots / 2;
-  if (E.cand_bytes == 0) E.cand_bytes = std::min<uint64_t>(free_b / 8, 4ull << 30);
+  if (E.cand_bytes == 0) E.cand_bytes = std::min<uint64_t>(free_b / 6, (E.world > 1 ? 24ull : 12ull) << 30);
   uint64_t rows_total = E.cand_bytes / (ROW * 8);
   E.region_rows = rows_total / E.world;
   if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
@@ -757,7 +850,7 @@ static int launch_invariants(Engine& E, uint64_t first, uint64_t count_bound) {
   return KMC_OK;
 }
 
-static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
+static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool fused = false) {
   Params p = E.params();
   // small levels: fewer states per thread so that every SM still gets a tile
   int spt = EXPAND_SPT;
@@ -767,13 +860,17 @@ static int launch_expand(Engine& E, uint64_t first, uint64_t count) {
   const size_t smem = (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  grid *= EXPAND_MIN_BLOCKS;
+  if ((uint64_t)grid > tiles) grid = (int)std::max<uint64_t>(tiles, 1);
   TimedLaunch t(E, 0);
-  if (E.world > 1) k_expand<true><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
-  else k_expand<false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
+  if (E.world > 1) k_expand<true, false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
+  else if (fused) k_expand<false, true><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
+  else k_expand<false, false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
   CK(cudaGetLastError());
   return KMC_OK;
 }
@@ -864,11 +961,19 @@ static int engine_run(Engine& E) {
   }
   while (!err && !stopped && level_end > level_first) {
     E.widths.push_back(level_end - level_first);
-    for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
-      uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+    if (E.fused) {
+      // one launch per level: successors are inserted from the expand kernel's staged flush; only
+      // rows that overflowed a warp's stage (rare bursts) go through cand + k_insert
       if ((rc = reset_cand(E))) return rc;
-      if ((rc = launch_expand(E, off, cnt))) return rc;
-      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)M::MAX_FANOUT))) return rc;
+      if ((rc = launch_expand(E, level_first, level_end - level_first, true))) return rc;
+      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, 32 * 1024))) return rc;
+    } else {
+      for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
+        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+        if ((rc = reset_cand(E))) return rc;
+        if ((rc = launch_expand(E, off, cnt))) return rc;
+        if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)M::MAX_FANOUT))) return rc;
+      }
     }
     if ((rc = launch_invariants(E, level_end, (level_end - level_first) * 2))) return rc;
     if ((rc = read_counters(E, &h))) return rc;
@@ -892,6 +997,10 @@ static int engine_run(Engine& E) {
     level_first = level_end;
     level_end = h.store_tail;
     ++level;
+    if (E.stop_after_states && h.store_tail >= E.stop_after_states && level_end > level_first) {
+      stopped = true;          // bounded throughput run: the queue is reported, no error
+      break;
+    }
   }
   CK(cudaEventRecord(E.ev_end, E.stream));
   CK(cudaStreamSynchronize(E.stream));
@@ -942,6 +1051,8 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "check_deadlock", &b)) E.check_deadlock = b;
   if (json_bool(options_json, "timing", &b)) E.timing = b;
   if (json_bool(options_json, "count_actions", &b)) E.count_actions = b;
+  if (json_bool(options_json, "fused", &b)) E.fused = b;
+  if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
   if (E.world < 1 || E.world > MAX_WORLD || E.rank >= E.world || (E.table_log2 && (E.table_log2 < 4 || E.table_log2 > 34))) {
     delete c;
     return KMC_E_BADARG;

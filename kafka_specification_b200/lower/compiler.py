@@ -344,6 +344,10 @@ class Lowerer:
             return True
         if is_const(a) and is_const(b):
             return self.const_eq(a, b)
+        ca, cb = self.enc_cache.get(id(a)), self.enc_cache.get(id(b))
+        if ca is not None and cb is not None and ca[1] is a and cb[1] is b and ca[0] is cb[0]:
+            # both were decoded from codes of the same (injective) layout type: compare the codes
+            return True if ca[2] == cb[2] else SBool(self.tmp_bool(f"({ca[2]} == {cb[2]})"))
         if isinstance(a, SUnion) or isinstance(b, SUnion):
             terms = []
             for ga, xa in self.alts(a):
@@ -519,7 +523,7 @@ class Lowerer:
         """set_items with every element guarded against an equal earlier element, so that an
         enumeration visits each member of the (runtime) set exactly once."""
         items = self.set_items(s)
-        if isinstance(s, frozenset) or isinstance(s, SLazy):
+        if isinstance(s, frozenset) or isinstance(s, SLazy) or (isinstance(s, SSet) and s.distinct):
             return items
         out = []
         for i, (g, x) in enumerate(items):
@@ -772,14 +776,15 @@ class Lowerer:
             return SSet(items)
         if k == "setfilter":
             items = []
-            for g, x in self.set_items(self.ev(e[2], ctx, fm, env, S)):
+            src_set = self.ev(e[2], ctx, fm, env, S)
+            for g, x in self.set_items(src_set):
                 env2 = dict(env)
                 env2[e[1]] = x
                 items.append((self.b_and([g, self.ev_bool(e[3], ctx, fm, env2, S)]), x))
             items = [(g, x) for g, x in items if g is not False]
             if all(g is True and is_const(x) for g, x in items):
                 return frozenset(x for _, x in items)
-            return SSet(items)
+            return SSet(items, distinct=isinstance(src_set, (frozenset, SLazy)) or getattr(src_set, "distinct", False))
         if k == "subset":
             return SLazy("powerset", self.ev(e[1], ctx, fm, env, S))
         if k == "domain":
@@ -884,11 +889,13 @@ class Lowerer:
         if op == "\\intersect":
             if isinstance(a, frozenset) and isinstance(b, frozenset):
                 return a & b
-            return SSet([(self.b_and([g, self.member(x, b)]), x) for g, x in self.set_items(a)])
+            return SSet([(self.b_and([g, self.member(x, b)]), x) for g, x in self.set_items(a)],
+                        distinct=isinstance(a, (frozenset, SLazy)) or getattr(a, "distinct", False))
         if op == "\\":
             if isinstance(a, frozenset) and isinstance(b, frozenset):
                 return a - b
-            return SSet([(self.b_and([g, self.b_not(self.member(x, b))]), x) for g, x in self.set_items(a)])
+            return SSet([(self.b_and([g, self.b_not(self.member(x, b))]), x) for g, x in self.set_items(a)],
+                        distinct=isinstance(a, (frozenset, SLazy)) or getattr(a, "distinct", False))
         if op == "<=>":
             return self.eq(self.ev_bool(e[2], ctx, fm, env, S), self.ev_bool(e[3], ctx, fm, env, S))
         raise LowerError(f"unsupported operator {op}")

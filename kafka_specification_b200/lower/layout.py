@@ -574,7 +574,7 @@ class TSet(Ty):
     def dec(self, lw, code):
         if not self.card:
             return super().dec(lw, code)
-        return SSet([(SBool(f"(({code} >> {j}) & 1u)"), self.elem.py_dec(j)) for j in range(self.elem.card)])
+        return SSet([(SBool(f"(({code} >> {j}) & 1u)"), self.elem.py_dec(j)) for j in range(self.elem.card)], distinct=True)
 
     def _items(self, lw, v):
         if isinstance(v, frozenset):
@@ -610,14 +610,14 @@ class TSet(Ty):
             for i, a in enumerate(self.chunks):
                 for j in range(a.bits):
                     items.append((SBool(f"((a{a.index} >> {j}) & 1u)"), self.elem.py_dec(32 * i + j)))
-            return SSet(items)
+            return SSet(items, distinct=True)
         items = []
         for i, a in enumerate(self.slots):
             g = SBool(f"({i} < (int)a{self.count_atom.index})")
             x = self.elem.dec(lw, f"a{a.index}")
             lw.enc_cache[id(x)] = (self.elem, x, f"(int)a{a.index}")     # re-encoding x is the identity
             items.append((g, x))
-        return SSet(items)
+        return SSet(items, distinct=True)            # canonical array: sorted, no duplicates
 
     def write(self, lw, v, out):
         if self.cap is None:

@@ -74,10 +74,11 @@ class SFn:
 
 
 class SSet:
-    __slots__ = ("items",)
+    __slots__ = ("items", "distinct")
 
-    def __init__(self, items: list):
+    def __init__(self, items: list, distinct: bool = False):
         self.items = [(g, x) for g, x in items if g is not False]
+        self.distinct = distinct      # True: no two present elements are equal (canonical layouts, filters of them)
 
     def __repr__(self):
         return f"SSet({self.items})"

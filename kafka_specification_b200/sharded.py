@@ -222,6 +222,15 @@ class ShardedChecker:
             e.insert_received(rows)
 
     # -- the search ------------------------------------------------------------
+    def _level_summary(self, count: int) -> tuple[int, int, int]:
+        """One collective per level: (total new states, any violation, max #chunks over ranks)."""
+        e = self.e
+        my_chunks = (count + e.chunk_states - 1) // e.chunk_states
+        if self.world == 1:
+            return count, 1 if e.violation() else 0, my_chunks
+        rows = self._all_gather_counts([count, 1 if e.violation() else 0, my_chunks])
+        return sum(r[0] for r in rows), max(r[1] for r in rows), max(r[2] for r in rows)
+
     def run(self) -> ShardedResult:
         e = self.e
         self.exchanged = 0
@@ -233,19 +242,15 @@ class ShardedChecker:
         self._round(0, 0, init=True)
         first, count = e.level_done()
         levels: list[int] = []
-        complete, stopped = True, False
+        stopped = False
         while True:
-            total, viol = self._all_reduce([count, 1 if e.violation() else 0])
+            total, viol, n_chunks = self._level_summary(count)
             if viol and not self.cont:
                 stopped = True
-                if total:
-                    complete = False
                 break
             if total == 0:
                 break
             levels.append(total)
-            my_chunks = (count + e.chunk_states - 1) // e.chunk_states
-            n_chunks = self._all_reduce([my_chunks], op=dist.ReduceOp.MAX)[0] if self.world > 1 else my_chunks
             for c in range(n_chunks):
                 off = c * e.chunk_states
                 n = max(0, min(e.chunk_states, count - off))
@@ -253,14 +258,16 @@ class ShardedChecker:
             first, count = e.level_done()
         e.finish()
         st = e.stats()
-        sums = self._all_reduce([st["distinct"], st["generated"], st["deadlocks"]])
-        per_rank = self._all_gather_counts([st["distinct"]])
+        if self.world > 1:
+            rows = self._all_gather_counts([st["distinct"], st["generated"], st["deadlocks"]])
+        else:
+            rows = [[st["distinct"], st["generated"], st["deadlocks"]]]
         seconds = time.perf_counter() - t0
         if self.world > 1:
             seconds = self._all_reduce_max_float(seconds)
-        return ShardedResult(distinct=sums[0], generated=sums[1], depth=len(levels), deadlocks=sums[2], levels=levels,
-                             complete=complete and not stopped,
-                             violation=e.violation(), per_rank_distinct=[p[0] for p in per_rank], seconds=seconds,
+        return ShardedResult(distinct=sum(r[0] for r in rows), generated=sum(r[1] for r in rows), depth=len(levels),
+                             deadlocks=sum(r[2] for r in rows), levels=levels, complete=not stopped,
+                             violation=e.violation(), per_rank_distinct=[r[0] for r in rows], seconds=seconds,
                              exchanged_rows=self.exchanged, stats=st)
 
     def _all_reduce_max_float(self, x: float) -> float:

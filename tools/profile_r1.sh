@@ -11,3 +11,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_expand -s 21 -
 ncu --set full --clock-control none --import-source on -k regex:k_insert -s 22 -c 2 -f -o gpurun_out/prof_insert_${MODEL} \
     python tools/run_model.py $MODEL $ARGS > gpurun_out/prof_insert_${MODEL}.log 2>&1
 ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:k_invariants -s 22 -c 2 -f -o gpurun_out/prof_invariants_${MODEL} \
+    python tools/run_model.py $MODEL $ARGS > gpurun_out/prof_invariants_${MODEL}.log 2>&1
