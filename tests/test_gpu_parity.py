@@ -185,3 +185,51 @@ def _assert_trace_is_behaviour(name, trace, ck):
     wl = np.array(trace[-1]["words"], dtype=np.uint64)
     lib.kmc_host_first_violated.argtypes = [ctypes.c_void_p]
     assert lib.kmc_host_first_violated(wl.ctypes.data) >= 0
+
+
+@pytest.mark.parametrize("name,opts", [("kip320_3x4_r4e2", {"table_log2": 26, "max_states": 20_000_000}),
+                                       ("kip320_3x4_r3e3", {"table_log2": 28, "max_states": 70_000_000})])
+def test_headline_sizes_match_oracle_b_golden(name, opts, goldens):
+    """Full-size runs (10^7..10^8 states): counts and per-level widths against the committed Oracle B golden."""
+    g = goldens[name]
+    with checker(name, **opts) as ck:
+        r = ck.run()
+    assert r.complete and r.violation is None
+    assert (r.distinct, r.generated, r.depth, r.deadlocks) == (g["distinct"], g["generated"], g["depth"], g["deadlocks"])
+    assert r.levels == g["levels"]
+
+
+def test_fused_and_unfused_paths_agree(goldens):
+    g = goldens["kip320_small"]
+    for fused in (False, True):
+        with checker("kip320_small", fused=fused) as ck:
+            r = ck.run()
+        assert (r.distinct, r.generated, r.depth, r.levels) == (g["distinct"], g["generated"], g["depth"], g["levels"])
+
+
+def test_bounded_run_stops_cleanly():
+    """stop_after_states: a bounded throughput run ends at a level boundary with the queue reported."""
+    with checker("kip320_small", stop_after_states=100_000) as ck:
+        r = ck.run()
+    assert not r.complete and r.violation is None and r.queue > 0
+    assert r.distinct >= 100_000 and sum(r.levels) + r.queue == r.distinct
+
+
+def test_two_gpu_sharded_run_matches_golden(goldens):
+    """Fingerprint-sharded BFS over NCCL on 2 GPUs (skipped on a single-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                          "--gpus", "2", "--steps", "1", "--warmup", "3", "--model", "kip320_3x4_r4e2"],
+                         capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert line, out.stdout + out.stderr
+    r = json.loads(line[-1])
+    g = goldens["kip320_3x4_r4e2"]
+    assert r["config"]["distinct"] == g["distinct"] and r["config"]["generated"] == g["generated"]
+    assert sum(r["config"]["per_rank_distinct"]) == g["distinct"]
