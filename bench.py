@@ -237,8 +237,11 @@ def run_single(args):
     def roof(kernel, bytes_per_bfs, total_ms, n_launch):
         sec = total_ms / 1000.0
         ach = steps * bytes_per_bfs / sec / 1e9 if sec > 0 else 0.0
+        ratio = (traffic.get(kernel) or {}).get("traffic_over_algorithmic")
+        per_launch = steps * bytes_per_bfs / max(1, n_launch)
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic.get(kernel), "peak_source": peak_src,
+                "traffic": (ratio * per_launch) if ratio else None, "traffic_over_algorithmic": ratio,
+                "peak_source": peak_src,
                 "avg_launch_ms": total_ms / max(1, n_launch), "launches": n_launch,
                 "algorithmic_bytes_per_launch": steps * bytes_per_bfs / max(1, n_launch),
                 "share_of_gpu_time": total_ms / max(1e-9, sum(gpu_ms))}

@@ -104,7 +104,8 @@ typedef struct {
  * optional: "device":0, "table_log2":27, "max_states":N, "cand_bytes":N, "rank":0, "world":1,
  * "continue":false, "check_deadlock":true|false (override), "timing":true,
  * "fused":false (single GPU: insert from the expand kernel's staged flush; measured slower),
- * "stop_after_states":N (bounded run: stop at the first level end holding >= N states).        */
+ * "stop_after_states":N (bounded run: stop at the first level end holding >= N states),
+ * "stream":H (cudaStream_t handle of the caller to launch on instead of a private stream).        */
 int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out);
 void kmc_destroy(kmc_ctx* ctx);
 int kmc_model_info(const kmc_ctx* ctx, kmc_model_info_t* out);

@@ -590,6 +590,7 @@ struct Engine {
   bool fused = false;           // single-GPU kmc_run: insert from the expand kernel's staged flush (measured slower:
                                 // warps waiting on probe latency hold up the CTA-wide group barrier)
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
+  int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
 
   uint64_t* table = nullptr;
   uint64_t table_slots = 0;
@@ -602,6 +603,7 @@ struct Engine {
   DevCounters* ctr = nullptr;
   uint64_t* viol_ring = nullptr;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;       // false: the caller's stream (option "stream"), e.g. torch's current stream
   uint64_t chunk_states = 0;
 
   std::vector<cudaEvent_t> event_pool;
@@ -736,6 +738,7 @@ static int engine_alloc(Engine& E) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, E.device));
   E.sms = prop.multiProcessorCount;
+  if (E.l2_fetch) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)E.l2_fetch));
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   if (E.table_log2 == 0) {
@@ -751,7 +754,7 @@ static int engine_alloc(Engine& E) {
   E.region_rows = rows_total / E.world;
   if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
   E.chunk_states = std::max<uint64_t>(1, E.region_rows / M::MAX_FANOUT);
-  CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+  if (E.own_stream) CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&E.table, E.table_slots * 8));
   CK(cudaMalloc(&E.store, E.max_states * W * 8));
   CK(cudaMalloc(&E.parent, E.max_states * 8));
@@ -1053,6 +1056,13 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "count_actions", &b)) E.count_actions = b;
   if (json_bool(options_json, "fused", &b)) E.fused = b;
   if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
+  if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
+  if (json_num(options_json, "stream", &d) && d != 0) {
+    // a cudaStream_t handle of the calling process (e.g. torch.cuda.current_stream().cuda_stream): engine
+    // kernels are then ordered with the caller's own work (NCCL exchange) without host synchronisation
+    E.stream = reinterpret_cast<cudaStream_t>((uintptr_t)d);
+    E.own_stream = false;
+  }
   if (E.world < 1 || E.world > MAX_WORLD || E.rank >= E.world || (E.table_log2 && (E.table_log2 < 4 || E.table_log2 > 34))) {
     delete c;
     return KMC_E_BADARG;
@@ -1076,7 +1086,7 @@ void kmcm_destroy(kmcm_ctx* c) {
   for (cudaEvent_t ev : E.event_pool) cudaEventDestroy(ev);
   if (E.ev_begin) cudaEventDestroy(E.ev_begin);
   if (E.ev_end) cudaEventDestroy(E.ev_end);
-  if (E.stream) cudaStreamDestroy(E.stream);
+  if (E.stream && E.own_stream) cudaStreamDestroy(E.stream);
   delete c;
 }
 

@@ -145,7 +145,8 @@ class Lowerer:
         self.unit_id = 0
         self._unit_emit_mark = 0
         self.prologue: list[str] = []
-        self.enc_cache: dict[int, tuple] = {}          # id(sval) -> (type, sval, code expr) for values decoded from a code
+        self.enc_cache: dict[int, tuple] = {}          # id(sval) -> (type sig, sval, code expr) for values decoded from a code
+        self.mux_origin: dict[int, tuple] = {}         # id(sval) -> (sval, cond, a, b) for composite selects
 
     # ------------------------------------------------------------------ atoms
     def _intern_cfg_atoms(self):
@@ -252,6 +253,41 @@ class Lowerer:
     def trap_unless(self, cond):
         self.traps.append(cond)
 
+    # -- code cache: values that were decoded from a packed code can be re-encoded (and compared)
+    #    by that code instead of field by field; a select between such values is a select of codes
+    def remember_code(self, ty, v, code: str):
+        if not is_const(v):
+            self.enc_cache[id(v)] = (ty.sig(), v, code, self.cg.blocks[-1], self.unit_id)
+
+    def _code_hit(self, v):
+        hit = self.enc_cache.get(id(v))
+        if hit is None or hit[1] is not v:
+            return None
+        # a code expression may name temporaries: it is only usable inside the block (and unit) that made it
+        if hit[3] not in self.cg.blocks or not (hit[4] == self.unit_id or hit[4] == -2):
+            return None
+        return hit
+
+    def encode(self, ty, v) -> str:
+        """ty.enc(v), short-circuited through the code cache and through recorded selects."""
+        if is_const(v):
+            return ty.enc(self, v)
+        hit = self._code_hit(v)
+        if hit is not None and hit[0] == ty.sig():
+            return hit[2]
+        m = self.mux_origin.get(id(v))
+        if m is not None and m[0] is v:
+            _, c, a, b = m
+            marks = len(self.traps)
+            ea = self.encode(ty, a)
+            eb = self.encode(ty, b)
+            if len(self.traps) == marks:          # no range traps were needed for either branch
+                code = self.tmp_int(f"({c.s} ? {ea} : {eb})")
+                self.remember_code(ty, v, code)
+                return code
+            del self.traps[marks:]
+        return ty.enc(self, v)
+
     # ---------------------------------------------------------- value helpers
     def as_sint(self, v) -> SInt:
         if isinstance(v, SInt):
@@ -344,8 +380,8 @@ class Lowerer:
             return True
         if is_const(a) and is_const(b):
             return self.const_eq(a, b)
-        ca, cb = self.enc_cache.get(id(a)), self.enc_cache.get(id(b))
-        if ca is not None and cb is not None and ca[1] is a and cb[1] is b and ca[0] is cb[0]:
+        ca, cb = self._code_hit(a), self._code_hit(b)
+        if ca is not None and cb is not None and ca[0] == cb[0]:
             # both were decoded from codes of the same (injective) layout type: compare the codes
             return True if ca[2] == cb[2] else SBool(self.tmp_bool(f"({ca[2]} == {cb[2]})"))
         if isinstance(a, SUnion) or isinstance(b, SUnion):
@@ -420,7 +456,15 @@ class Lowerer:
             return a
         ka, kb = kind_sig(a), kind_sig(b)
         if ka == "union" or kb == "union" or ka != kb:
-            return self.union_merge(c, a, b)
+            res = self.union_merge(c, a, b)
+            if not is_const(res):
+                self.mux_origin[id(res)] = (res, c, a, b)
+            return res
+        if ka.startswith("rec:"):
+            fa, fb = self.rec_fields(a), self.rec_fields(b)
+            res = SRec({f: self.mux(c, fa[f], fb[f]) for f in fa})
+            self.mux_origin[id(res)] = (res, c, a, b)
+            return res
         if ka == "int":
             A, B = self.as_sint(a), self.as_sint(b)
             if A.s == B.s:
@@ -1309,6 +1353,7 @@ class Lowerer:
         self.cg = CG()
         self.read_cache = {}
         self.enc_cache = {}
+        self.mux_origin = {}
         self.unit_id = -2                      # values forced while reading belong to the prologue
         self.cur = {v: self.read_ty(self.layout.var_types[v]) for v in self.variables}
         self.prologue = self.cg.lines

@@ -94,6 +94,14 @@ class Layout:
 # ---------------------------------------------------------------------------
 class Ty:
     card: int = 0          # number of values if the type is codeable as one integer, else 0
+    _sig = None
+
+    def sig(self) -> str:
+        """Structural identity of the encoding: equal sig <=> equal value/code mapping."""
+        if self._sig is None:
+            import json
+            self._sig = json.dumps(self.describe(), sort_keys=True)
+        return self._sig
 
     def alloc(self, lay: Layout, path: str):
         raise NotImplementedError
@@ -127,12 +135,14 @@ class Ty:
     def read(self, lw):
         if self.atom is None:
             return self.py_dec(0)
-        return self.dec(lw, f"a{self.atom.index}")
+        v = self.dec(lw, f"a{self.atom.index}")
+        lw.remember_code(self, v, f"a{self.atom.index}")
+        return v
 
     def write(self, lw, v, out: dict):
         if self.atom is None:
             return
-        out[self.atom.index] = self.enc(lw, v)
+        out[self.atom.index] = lw.encode(self, v)
 
     def _alloc_scalar(self, lay: Layout, path: str):
         b = bits_for(self.card)
@@ -296,7 +306,7 @@ class TRec(Ty):
         self._check(v)
         terms, stride = [], 1
         for f, t in self.fields.items():
-            c = t.enc(lw, self._get(v, f))
+            c = lw.encode(t, self._get(v, f))
             terms.append(c if stride == 1 else f"{c} * {stride}")
             stride *= t.card
         return lw.tmp_int("(" + " + ".join(terms) + ")")
@@ -387,7 +397,7 @@ class TFn(Ty):
             return str(self.py_enc(v))
         terms, stride = [], 1
         for t, x in zip(self.elems, self._vals(v)):
-            c = t.enc(lw, x)
+            c = lw.encode(t, x)
             terms.append(c if stride == 1 else f"{c} * {stride}")
             stride *= t.card
         return lw.tmp_int("(" + " + ".join(terms) + ")")
@@ -460,13 +470,13 @@ class TUnion(Ty):
         if isinstance(v, SUnion):
             e = None
             for g, x in reversed(v.alts):
-                c = self.enc(lw, x)
+                c = lw.encode(self, x)
                 e = c if e is None else f"({lw.bstr(g)} ? {c} : {e})"
             return lw.tmp_int(e if e is not None else "0")
         i = self._alt_for_kind(kind_sig(v))
         if i is None:
             raise LowerError(f"value {v!r} fits no alternative of {self.describe()}")
-        c = self.alts[i].enc(lw, v)
+        c = lw.encode(self.alts[i], v)
         return lw.tmp_int(f"({c} + {self.offsets[i]})" if self.offsets[i] else c)
 
     def dec(self, lw, code):
@@ -595,7 +605,7 @@ class TSet(Ty):
                 bit = f"{1 << (j % 32)}u"
                 terms[j // 32].append(bit if g is True else f"({g.s} ? {bit} : 0u)")
             else:
-                c = self.elem.enc(lw, x)
+                c = lw.encode(self.elem, x)
                 gs = lw.bstr(g)
                 if nchunks == 1:
                     terms[0].append(f"({gs} ? (1u << {c}) : 0u)")
@@ -615,7 +625,7 @@ class TSet(Ty):
         for i, a in enumerate(self.slots):
             g = SBool(f"({i} < (int)a{self.count_atom.index})")
             x = self.elem.dec(lw, f"a{a.index}")
-            lw.enc_cache[id(x)] = (self.elem, x, f"(int)a{a.index}")     # re-encoding x is the identity
+            lw.remember_code(self.elem, x, f"a{a.index}")               # re-encoding x is the identity
             items.append((g, x))
         return SSet(items, distinct=True)            # canonical array: sorted, no duplicates
 
@@ -641,11 +651,7 @@ class TSet(Ty):
         items = self._items(lw, v)
         cs = []
         for _, x in items:
-            hit = lw.enc_cache.get(id(x))
-            if hit is not None and hit[0] is self.elem and hit[1] is x:
-                cs.append(hit[2])
-            else:
-                cs.append(lw.tmp_int(self.elem.enc(lw, x)))
+            cs.append(lw.tmp_int(lw.encode(self.elem, x)))
         ps: list[str] = []
         for i, (g, _) in enumerate(items):
             terms = [lw.bstr(g)] + [f"!({ps[j]} && {cs[j]} == {cs[i]})" for j in range(i)]

@@ -65,9 +65,15 @@ class CudaShardEngine(ShardEngine):
     """One rank of the CUDA engine, driven through the kmc_shard_* entry points."""
 
     def __init__(self, model: str, rank: int, world: int, device: int, **options):
+        self.device = torch.device("cuda", device)
+        # run the engine on a torch stream that is also the current stream of every collective the
+        # driver issues: kernels and the NCCL exchange then order themselves on the device, the host
+        # only synchronises where it needs a value.  (The legacy default stream has handle 0 and
+        # cannot be passed, hence a dedicated stream.)
+        self.stream = torch.cuda.Stream(self.device)
+        options.setdefault("stream", self.stream.cuda_stream)
         self.ck = Checker(model, device=device, rank=rank, world=world, **options)
         self.rank, self.world = rank, world
-        self.device = torch.device("cuda", device)
         self.lib = self.ck.lib
         b = ShardBuffers()
         self.ck._check(self.lib.kmc_shard_buffers(self.ck.ctx, ctypes.byref(b)))
@@ -81,6 +87,8 @@ class CudaShardEngine(ShardEngine):
                      if world > 1 else self.cand)
         self._recv_ptr = b.recv if world > 1 else b.cand
         self._cand_ptr = b.cand
+        self.counts_dev = torch.as_tensor(_DevArray(b.cand_counts, 8), device=self.device)[:world]
+        self._matrix = torch.empty(world * world, dtype=torch.int64, device=self.device)
 
     def begin(self):
         self.ck._check(self.lib.kmc_shard_begin(self.ck.ctx))
@@ -95,6 +103,13 @@ class CudaShardEngine(ShardEngine):
         buf = (ctypes.c_uint64 * 8)()
         self.ck._check(self.lib.kmc_shard_counts(self.ck.ctx, buf))
         return [int(buf[d]) for d in range(self.world)]
+
+    def count_matrix(self, group=None):
+        """world x world matrix of rows produced per (source, owner): one collective on the device
+        counters, one device->host copy (the only host synchronisation of a round)."""
+        dist.all_gather_into_tensor(self._matrix, self.counts_dev, group=group)
+        m = self._matrix.cpu().tolist()
+        return [m[r * self.world:(r + 1) * self.world] for r in range(self.world)]
 
     def send_view(self, dest, rows):
         off = dest * self.region_rows * self.row_words
@@ -178,9 +193,10 @@ class ShardedChecker:
         dist.all_reduce(t, op=op, group=self.group)
         return t.tolist()
 
-    def _exchange(self, counts: list[int]) -> int:
+    def _exchange(self, counts, matrix=None) -> int:
         """all-to-all-v of candidate rows; returns the number of rows now in the recv buffer."""
-        matrix = self._all_gather_counts(counts)           # matrix[src][dst]
+        if matrix is None:
+            matrix = self._all_gather_counts(counts)       # matrix[src][dst]
         incoming = [matrix[src][self.rank] for src in range(self.world)]
         self.e.reserve_recv(sum(incoming))
         ops, off = [], 0
@@ -200,8 +216,6 @@ class ShardedChecker:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        if self.e.device.type == "cuda":
-            torch.cuda.current_stream(self.e.device).synchronize()
         self.exchanged += sum(counts) - counts[self.rank]
         return off
 
@@ -212,12 +226,17 @@ class ShardedChecker:
             e.reset_cand()
             if count:
                 e.expand(first, count)
-        counts = e.counts()
         if self.world == 1:
+            counts = e.counts()
             if counts[0]:
                 e.insert_local(counts[0])
             return
-        rows = self._exchange(counts)
+        if hasattr(e, "count_matrix"):
+            matrix = e.count_matrix(self.group)
+            counts = matrix[self.rank]
+        else:
+            matrix, counts = None, e.counts()
+        rows = self._exchange(counts, matrix)
         if rows:
             e.insert_received(rows)
 
@@ -232,6 +251,13 @@ class ShardedChecker:
         return sum(r[0] for r in rows), max(r[1] for r in rows), max(r[2] for r in rows)
 
     def run(self) -> ShardedResult:
+        stream = getattr(self.e, "stream", None)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                return self._run()
+        return self._run()
+
+    def _run(self) -> ShardedResult:
         e = self.e
         self.exchanged = 0
         if self.world > 1:
