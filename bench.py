@@ -248,6 +248,17 @@ def run_single(args):
 
     r_exp = roof("k_expand", exp_bytes, exp_ms, n_exp)
     r_ins = roof("k_insert", ins_bytes, ins_ms, n_ins)
+    # secondary denominator for the hash-probe kernel: measured random 32 B-sector gather rate on a table
+    # of the same size (tools/gather_bench.cu -> profiles/gather_peak.json)
+    gp = os.path.join(ROOT, "profiles", "gather_peak.json")
+    if os.path.exists(gp) and ins_ms > 0:
+        want = res.stats["table_slots"] * 8
+        pts = load_json(gp)["results"]
+        best = min(pts, key=lambda r: abs(r["table_bytes"] - want))
+        probes_per_s = steps * res.stats["probes"] / (ins_ms / 1000.0)
+        r_ins["random_gather_peak_probes_per_s"] = best["probes_per_s"]
+        r_ins["probes_per_s"] = probes_per_s
+        r_ins["frac_of_random_gather_peak"] = probes_per_s / best["probes_per_s"]
     r_inv = roof("k_invariants", inv_bytes, inv_ms, n_inv)
     ranked = sorted([r_exp, r_ins, r_inv], key=lambda r: -r["share_of_gpu_time"])
     dominant, other = ranked[0], ranked[1:]
