@@ -50,7 +50,8 @@ enum {
   KMC_E_LAYOUT_OVERFLOW = -6, /* a successor value does not fit the packed state layout  */
   KMC_E_MODEL = -7,           /* cannot load / mismatching lowered model library         */
   KMC_E_STATE = -8,           /* call sequence error (e.g. trace before run)             */
-  KMC_E_NO_GPU = -9           /* no CUDA device: there is deliberately no CPU fallback   */
+  KMC_E_NO_GPU = -9,          /* no CUDA device: there is deliberately no CPU fallback   */
+  KMC_E_CAND_FULL = -10       /* candidate buffer overflow (raise cand_bytes / fanout_bound) */
 };
 
 /* result kinds (kmc_violation_t.kind); a driver maps them to TLC's exit codes 0/12/11 */
@@ -105,7 +106,9 @@ typedef struct {
  * "continue":false, "check_deadlock":true|false (override), "timing":true,
  * "fused":false (single GPU: insert from the expand kernel's staged flush; measured slower),
  * "stop_after_states":N (bounded run: stop at the first level end holding >= N states),
- * "stream":H (cudaStream_t handle of the caller to launch on instead of a private stream).        */
+ * "stream":H (cudaStream_t handle of the caller to launch on instead of a private stream),
+ * "fanout_bound":K (successors per state assumed when sizing frontier chunks; default min(MAX_FANOUT, 32)),
+ * "two_phase":false (guard phase + compacted body phase variant of the expand kernel).            */
 int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out);
 void kmc_destroy(kmc_ctx* ctx);
 int kmc_model_info(const kmc_ctx* ctx, kmc_model_info_t* out);

@@ -439,6 +439,190 @@ struct GroupRunner<M::NUM_GROUPS, MULTI, FUSED> {
                                               uint64_t*, unsigned*, ExpandStats&) {}
 };
 
+// ----------------------------------------------------------------------------------------
+// K1, two-phase form.  ncu's source page showed that 52 % of the instructions the one-phase kernel
+// issues run with <= 3 active lanes: they sit inside action bodies that only a few of a warp's 32
+// states enable.  Here every group is processed in two phases:
+//   A  all lanes evaluate item_guard (the cheap leading guards of each top-level block) on their own
+//      states; enabled (item, state) pairs are appended to a CTA-wide list in shared memory
+//      (ballot + one shared-memory atomic per warp);
+//   B  the list -- nearly sorted by item, because the CTA walks the items in lockstep -- is consumed
+//      32 entries at a time: each lane loads "its" state and runs item_body, so the expensive
+//      successor construction runs with (almost) all lanes on (almost) the same code.
+// ----------------------------------------------------------------------------------------
+static constexpr int LIST_CAP = 16384;
+
+struct TwoPhaseCtx {
+  uint64_t first, tile_base, count;
+  int spt;
+  uint64_t* wbuf;
+  unsigned* wcnt;
+  unsigned* list;        // [LIST_CAP]
+  unsigned* list_count;
+  unsigned* succ;        // successors per tile state [EXPAND_BLOCK * EXPAND_SPT]
+};
+
+// Each item body is its own (non-inlined) function: inlining all bodies of a group into the
+// dispatch chain lets the compiler hoist every body's unpacking above the chain, which blows the
+// 64-register budget of a 1024-thread CTA (2 KB of spills measured).
+template <int I, class Sink>
+__device__ __noinline__ void item_body_call(const State& s, Sink& sink) {
+  M::item_body(M::ItemTag<I>{}, s, sink);
+}
+
+template <int I, int END>
+struct ItemDispatch {
+  template <class Sink>
+  static __device__ __forceinline__ void run(int item, const State& s, Sink& sink) {
+    if (item == I) {
+      item_body_call<I, Sink>(s, sink);
+      return;
+    }
+    ItemDispatch<I + 1, END>::run(item, s, sink);
+  }
+};
+template <int END>
+struct ItemDispatch<END, END> {
+  template <class Sink>
+  static __device__ __forceinline__ void run(int, const State&, Sink&) {}
+};
+
+template <int I, int END, int BEGIN, bool MULTI>
+struct ItemGuards {
+  static __device__ __forceinline__ void run(const Params& p, const TwoPhaseCtx& c, int& failed) {
+    const unsigned lane = lane_id();
+#pragma unroll 1
+    for (int j = 0; j < c.spt; ++j) {
+      const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
+      const uint64_t i = c.tile_base + loc;
+      bool en = false;
+      State s;
+      if (i < c.count) {
+        load_state(s, p.store + (c.first + i) * W);
+        en = M::item_guard(M::ItemTag<I>{}, s);
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, en);
+      if (mask) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(c.list_count, (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (en) {
+          unsigned pos = base + __popc(mask & ((1u << lane) - 1));
+          if (pos < (unsigned)LIST_CAP) {
+            c.list[pos] = ((unsigned)(I - BEGIN) << 16) | loc;
+          } else {
+            // list full (a group in which nearly everything is enabled): run the body right here
+            CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
+            item_body_call<I, CandSink<MULTI>>(s, sink);
+            if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
+            failed |= sink.failed;
+          }
+        }
+      }
+    }
+    ItemGuards<I + 1, END, BEGIN, MULTI>::run(p, c, failed);
+  }
+};
+template <int END, int BEGIN, bool MULTI>
+struct ItemGuards<END, END, BEGIN, MULTI> {
+  static __device__ __forceinline__ void run(const Params&, const TwoPhaseCtx&, int&) {}
+};
+
+template <int G, bool MULTI>
+struct GroupRunner2 {
+  static __device__ __forceinline__ void run(const Params& p, const TwoPhaseCtx& c, int& failed, ExpandStats& xs) {
+    constexpr int BEGIN = M::GROUP_ITEM_BEGIN[G];
+    constexpr int END = M::GROUP_ITEM_BEGIN[G + 1];
+    __syncthreads();                                   // previous group's list fully consumed and reset
+    ItemGuards<BEGIN, END, BEGIN, MULTI>::run(p, c, failed);
+    __syncthreads();                                   // list complete
+    unsigned total = *c.list_count;
+    if (total > (unsigned)LIST_CAP) total = LIST_CAP;
+    const unsigned lane = lane_id();
+    const unsigned warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (unsigned e0 = warp * 32; e0 < total; e0 += EXPAND_BLOCK) {
+      const unsigned e = e0 + lane;
+      if (e < total) {
+        const unsigned entry = c.list[e];
+        const unsigned loc = entry & 0xFFFFu;
+        const uint64_t i = c.tile_base + loc;
+        State s;
+        load_state(s, p.store + (c.first + i) * W);
+        CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
+        ItemDispatch<BEGIN, END>::run((int)(entry >> 16) + BEGIN, s, sink);
+        if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
+        failed |= sink.failed;
+      }
+      flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *c.list_count = 0;
+    GroupRunner2<G + 1, MULTI>::run(p, c, failed, xs);
+  }
+};
+template <bool MULTI>
+struct GroupRunner2<M::NUM_GROUPS, MULTI> {
+  static __device__ __forceinline__ void run(const Params&, const TwoPhaseCtx&, int&, ExpandStats&) {}
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand2(Params p, uint64_t first, uint64_t count, int spt) {
+  extern __shared__ uint64_t stage[];   // [warps][STAGE_ROWS][ROW] | wcnt[warps] | list_count | list[LIST_CAP] | succ[TILE]
+  const int warp = threadIdx.x >> 5;
+  constexpr int NW = EXPAND_BLOCK / 32;
+  uint64_t* wbuf = stage + (size_t)warp * STAGE_ROWS * ROW;
+  unsigned* u = reinterpret_cast<unsigned*>(stage + (size_t)NW * STAGE_ROWS * ROW);
+  unsigned* wcnt = u + warp;
+  unsigned* list_count = u + NW;
+  unsigned* list = u + NW + 4;
+  unsigned* succ = list + LIST_CAP;
+  if (lane_id() == 0) *wcnt = 0;
+  if (threadIdx.x == 0) *list_count = 0;
+  unsigned long long gen = 0, dead = 0;
+  unsigned maxfan = 0;
+  int failed = 0;
+  ExpandStats xs{0, 0};
+  const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
+  for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
+    for (int j = 0; j < spt; ++j) succ[j * EXPAND_BLOCK + threadIdx.x] = 0;
+    TwoPhaseCtx c{first, tile_base, count, spt, wbuf, wcnt, list, list_count, succ};
+    GroupRunner2<0, MULTI>::run(p, c, failed, xs);
+    flush_stage<MULTI, false>(p, wbuf, wcnt, true, failed, xs);
+    __syncthreads();                                   // every body of this tile has added to succ[]
+#pragma unroll 1
+    for (int j = 0; j < spt; ++j) {
+      const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
+      uint64_t i = tile_base + loc;
+      if (i >= count) continue;
+      const unsigned n = succ[loc];
+      gen += n;
+      if (n > maxfan) maxfan = n;
+      if (n == 0) {
+        ++dead;
+        if (p.check_deadlock) {
+          State s;
+          load_state(s, p.store + (first + i) * W);
+          record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+        }
+      }
+    }
+    __syncthreads();                                   // succ[] is re-zeroed by the next tile
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    gen += __shfl_xor_sync(0xffffffffu, gen, o);
+    dead += __shfl_xor_sync(0xffffffffu, dead, o);
+    maxfan = max(maxfan, __shfl_xor_sync(0xffffffffu, maxfan, o));
+    failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
+  }
+  if (lane_id() == 0) {
+    if (gen) atomicAdd(&p.ctr->generated, gen);
+    if (dead) atomicAdd(&p.ctr->deadlocks, dead);
+    if (maxfan) atomicMax(&p.ctr->max_fanout_seen, (unsigned long long)maxfan);
+    if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
+  }
+}
+
 #ifndef EXPAND_MIN_BLOCKS
 #define EXPAND_MIN_BLOCKS 1
 #endif
@@ -591,6 +775,10 @@ struct Engine {
                                 // warps waiting on probe latency hold up the CTA-wide group barrier)
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
+  uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
+  bool two_phase = false;           // K1 as guard phase + compacted body phase (k_expand2): correct, lanes/inst 12 -> 25,
+                                    // but 2.3x slower as built (per-item re-unpack in the guard phase, local-memory
+                                    // traffic of the non-inlined bodies); kept as an opt-in path, see profiles/README.md
 
   uint64_t* table = nullptr;
   uint64_t table_slots = 0;
@@ -753,7 +941,12 @@ static int engine_alloc(Engine& E) {
   uint64_t rows_total = E.cand_bytes / (ROW * 8);
   E.region_rows = rows_total / E.world;
   if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
-  E.chunk_states = std::max<uint64_t>(1, E.region_rows / M::MAX_FANOUT);
+  // A chunk of frontier states is sized for `fanout_bound` successors per state on average *per owner region*.
+  // MAX_FANOUT (emit sites in expand) is a safe but very loose bound -- reachable states enable a small
+  // fraction of the sites (max 15 successors seen on the Kafka models, MAX_FANOUT ~100); the default
+  // assumes <= 32 and relies on the kernel's overflow check (KMC_E_CAND_FULL, nothing is lost silently).
+  if (E.fanout_bound == 0) E.fanout_bound = std::min<uint32_t>((uint32_t)M::MAX_FANOUT, 32u);
+  E.chunk_states = std::max<uint64_t>(1, E.region_rows / E.fanout_bound);
   if (E.own_stream) CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&E.table, E.table_slots * 8));
   CK(cudaMalloc(&E.store, E.max_states * W * 8));
@@ -801,6 +994,7 @@ static int fail_to_error(unsigned long long f) {
     case KMC_FAIL_LAYOUT: return KMC_E_LAYOUT_OVERFLOW;
     case KMC_FAIL_TABLE_FULL: return KMC_E_TABLE_FULL;
     case KMC_FAIL_STORE_FULL: return KMC_E_STORE_FULL;
+    case KMC_FAIL_CAND_FULL: return KMC_E_CAND_FULL;
     default: return KMC_E_CUDA;
   }
 }
@@ -870,6 +1064,20 @@ static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool fused =
   }
   grid *= EXPAND_MIN_BLOCKS;
   if ((uint64_t)grid > tiles) grid = (int)std::max<uint64_t>(tiles, 1);
+  if (E.two_phase && !fused) {
+    const size_t smem2 = smem + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4;
+    static bool attr2 = false;
+    if (!attr2) {
+      CK(cudaFuncSetAttribute(k_expand2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CK(cudaFuncSetAttribute(k_expand2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      attr2 = true;
+    }
+    TimedLaunch t(E, 0);
+    if (E.world > 1) k_expand2<true><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);
+    else k_expand2<false><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);
+    CK(cudaGetLastError());
+    return KMC_OK;
+  }
   TimedLaunch t(E, 0);
   if (E.world > 1) k_expand<true, false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
   else if (fused) k_expand<false, true><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
@@ -975,7 +1183,7 @@ static int engine_run(Engine& E) {
         uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
         if ((rc = reset_cand(E))) return rc;
         if ((rc = launch_expand(E, off, cnt))) return rc;
-        if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)M::MAX_FANOUT))) return rc;
+        if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
       }
     }
     if ((rc = launch_invariants(E, level_end, (level_end - level_first) * 2))) return rc;
@@ -1057,6 +1265,8 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "fused", &b)) E.fused = b;
   if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
   if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
+  if (json_bool(options_json, "two_phase", &b)) E.two_phase = b;
+  if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
     // a cudaStream_t handle of the calling process (e.g. torch.cuda.current_stream().cuda_stream): engine
     // kernels are then ordered with the caller's own work (NCCL exchange) without host synchronisation
@@ -1170,6 +1380,7 @@ const char* kmcm_strerror(const kmcm_ctx* c, int code) {
     case KMC_E_MODEL: return "cannot load the lowered model library";
     case KMC_E_STATE: return "call sequence error";
     case KMC_E_NO_GPU: return "no CUDA device visible; this library has no CPU fallback";
+    case KMC_E_CAND_FULL: return "candidate buffer overflow (raise cand_bytes or fanout_bound)";
     default: return "unknown error";
   }
 }

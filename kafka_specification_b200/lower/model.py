@@ -21,7 +21,7 @@ from . import layout as L
 from .compiler import Closure, Lowerer, Marker, Thunk
 from .svals import LowerError, SLazy, is_atom_const, is_const, is_int_const
 
-LOWERING_VERSION = 2
+LOWERING_VERSION = 3
 
 
 @dataclass
@@ -232,6 +232,100 @@ class TypeInference:
             f"'{var} \\in <finite type set>' (or '\\subseteq')")
 
 
+
+# ---------------------------------------------------------------------------
+# guard/body decomposition of the emitted units ("items")
+# ---------------------------------------------------------------------------
+class _Node:
+    __slots__ = ("text", "cond", "children", "is_block")
+
+    def __init__(self, text, cond=None, is_block=False):
+        self.text, self.cond, self.is_block, self.children = text, cond, is_block, []
+
+
+def _parse_unit(lines: list[str]) -> list[_Node]:
+    """Parses the emitter's own output (one statement / block head / '}' per line) into a tree."""
+    root = _Node("", is_block=True)
+    stack = [root]
+    for raw in lines:
+        t = raw.strip()
+        if t == "}":
+            stack.pop()
+        elif t.endswith("{"):
+            cond = t[len("if ("):-len(") {")] if t.startswith("if (") else None
+            n = _Node(t, cond, True)
+            stack[-1].children.append(n)
+            stack.append(n)
+        else:
+            stack[-1].children.append(_Node(t))
+    if len(stack) != 1:
+        raise LowerError("internal: unbalanced unit")
+    return root.children
+
+
+def _prune(nodes: list[_Node]) -> list[_Node]:
+    out = []
+    for n in nodes:
+        if n.is_block:
+            n.children = _prune(n.children)
+            if not n.children:
+                continue            # empty block (e.g. a statically dead disjunct)
+        out.append(n)
+    return out
+
+
+def _render(nodes: list[_Node], depth: int) -> list[str]:
+    out = []
+    for n in nodes:
+        if n.is_block:
+            out.append("  " * depth + n.text)
+            out.extend(_render(n.children, depth + 1))
+            out.append("  " * depth + "}")
+        else:
+            out.append("  " * depth + n.text)
+    return out
+
+
+def _unit_items(lines: list[str], max_prefix_temps: int = 3):
+    """Splits one unit into items.  An item = (guard temps, guard conditions, body lines): the
+    guard is the chain of leading `if`s that are preceded by at most a few temporaries -- cheap to
+    evaluate for every state; the body (which re-checks the chain) is the whole top-level block and
+    is executed only for the (state, item) pairs whose guard held, compacted across the CTA."""
+    nodes = _prune(_parse_unit(lines))
+    items = []
+    root_temps: list[_Node] = []
+    i = 0
+    while i < len(nodes):
+        n = nodes[i]
+        if not n.is_block:
+            root_temps.append(n)
+            i += 1
+            continue
+        group = [n]
+        while i + 1 < len(nodes) and not nodes[i + 1].is_block and nodes[i + 1].text.startswith("else "):
+            group.append(nodes[i + 1])
+            i += 1
+        conds, temps = [], []
+        cur = n
+        while True:
+            if cur.cond is not None:
+                conds.append(cur.cond)
+            kids = cur.children
+            lead = [k for k in kids if not k.is_block and k.text.startswith("const ")]
+            blocks = [k for k in kids if k.is_block]
+            others = [k for k in kids if not k.is_block and not k.text.startswith("const ")]
+            if len(blocks) == 1 and not others and len(lead) <= max_prefix_temps and kids[-1] is blocks[0] \
+                    and (blocks[0].cond is not None or not lead):
+                temps.extend(lead)
+                cur = blocks[0]
+                continue
+            break
+        items.append({"root_temps": _render(list(root_temps), 1), "guard_temps": _render(temps, 1),
+                      "conds": conds, "body": _render(group, 1)})
+        i += 1
+    return items
+
+
 # ---------------------------------------------------------------------------
 def _init_states(lw: Lowerer, init_expr) -> list[dict]:
     out: list[dict] = []
@@ -405,15 +499,22 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     # CUDA engine sweeps over a tile of states, so that its code stays resident in the SM's
     # instruction cache (a fully unrolled Next is hundreds of KB of SASS)
     groups: list[list[str]] = []
+    group_units: list[list[list[str]]] = []
     cur_lines: list[str] = []
+    cur_units: list[list[str]] = []
     for lines, _ in lw.units:
         if cur_lines and len(cur_lines) + len(lines) > group_lines:
             groups.append(cur_lines)
-            cur_lines = []
+            group_units.append(cur_units)
+            cur_lines, cur_units = [], []
         cur_lines = cur_lines + ["  {"] + ["  " + l for l in lines] + ["  }"]
+        cur_units.append(lines)
     if cur_lines or not groups:
         groups.append(cur_lines)
+        group_units.append(cur_units)
     expand_lines = [l for g in groups for l in g]
+    # guard/body items per group (consumed by the CUDA engine's two-phase expand kernel)
+    group_items = [[it for u in units for it in _unit_items(u)] for units in group_units]
     max_fanout = lw.emit_sites
 
     # invariants
@@ -467,6 +568,44 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     for gi in range(len(groups)):
         parts.append(f"  expand_group(GroupTag<{gi}>{{}}, s, sink);")
     parts.append("}")
+    # two-phase form of the same code: item_guard = cheap leading guards, item_body = the full block
+    parts.append("/* Two-phase form: an item is one top-level guarded block of a unit.  item_guard(I, s) evaluates only the")
+    parts.append("   cheap leading guards; item_body(I, s, sink) is the complete block (it re-checks them).  For every state,")
+    parts.append("   running item_body for exactly the items whose guard holds emits the same successors as expand(). */")
+    parts.append("template <int I> struct ItemTag {};")
+    n_items = 0
+    begins = []
+    for gi, items in enumerate(group_items):
+        begins.append(n_items)
+        for it in items:
+            parts.append(f"KMC_HD bool item_guard(ItemTag<{n_items}>, const State& s) {{")
+            parts.extend(unpack)
+            parts.extend(expand_prologue)
+            parts.extend(it["root_temps"])
+            parts.extend(it["guard_temps"])
+            parts.append("  return " + (" && ".join(f"({c})" for c in it["conds"]) if it["conds"] else "true") + ";")
+            parts.append("}")
+            parts.append(f"template <class Sink> KMC_HD void item_body(ItemTag<{n_items}>, const State& s, Sink& sink) {{")
+            parts.extend(unpack)
+            parts.extend(expand_prologue)
+            parts.extend(it["root_temps"])
+            parts.extend(it["body"])
+            parts.append("}")
+            n_items += 1
+    begins.append(n_items)
+    parts.append(f"static constexpr int NUM_ITEMS = {n_items};")
+    parts.append("static constexpr int GROUP_ITEM_BEGIN[NUM_GROUPS + 1] = {" + ", ".join(str(b) for b in begins) + "};")
+    parts.append("/* expand() through the two-phase form (used by tests to prove both forms agree) */")
+    parts.append("template <int I, int END> struct ItemLoop {")
+    parts.append("  template <class Sink> static KMC_HD void run(const State& s, Sink& sink) {")
+    parts.append("    if (item_guard(ItemTag<I>{}, s)) item_body(ItemTag<I>{}, s, sink);")
+    parts.append("    ItemLoop<I + 1, END>::run(s, sink);")
+    parts.append("  }")
+    parts.append("};")
+    parts.append("template <int END> struct ItemLoop<END, END> {")
+    parts.append("  template <class Sink> static KMC_HD void run(const State&, Sink&) {}")
+    parts.append("};")
+    parts.append("template <class Sink> KMC_HD void expand_items(const State& s, Sink& sink) { ItemLoop<0, NUM_ITEMS>::run(s, sink); }")
     parts.append("/* index of the first violated INVARIANT of the cfg, or -1 */")
     parts.append("KMC_HD int first_violated_invariant(const State& s) {")
     parts.extend(unpack)

@@ -80,7 +80,7 @@ class CudaShardEngine(ShardEngine):
         self.row_words = b.row_words
         self.region_rows = b.region_rows
         self.recv_rows_cap = b.recv_rows_cap
-        self.chunk_states = max(1, self.region_rows // self.ck.info.max_fanout)
+        self.chunk_states = max(1, self.region_rows // min(self.ck.info.max_fanout, int(options.get("fanout_bound", 32))))
         n_cand = self.region_rows * world * self.row_words
         self.cand = torch.as_tensor(_DevArray(b.cand, n_cand), device=self.device)
         self.recv = (torch.as_tensor(_DevArray(b.recv, self.recv_rows_cap * self.row_words), device=self.device)

@@ -20,7 +20,7 @@ BUILD = os.path.join(ROOT, "build", "hosttest")
 
 def build_host(model: LoweredModel) -> ctypes.CDLL:
     os.makedirs(BUILD, exist_ok=True)
-    tag = hashlib.sha256(model.header.encode()).hexdigest()[:16]
+    tag = hashlib.sha256((model.header + open(os.path.join(HERE, "host_bfs.cpp")).read()).encode()).hexdigest()[:16]
     hdr = os.path.join(BUILD, f"{model.name}_{tag}.h")
     so = os.path.join(BUILD, f"{model.name}_{tag}.so")
     if not os.path.exists(so):
@@ -33,8 +33,9 @@ def build_host(model: LoweredModel) -> ctypes.CDLL:
     return lib
 
 
-def run_host(model: LoweredModel, max_states: int = 0, dump: bool = False) -> dict:
+def run_host(model: LoweredModel, max_states: int = 0, dump: bool = False, items: bool = False) -> dict:
     lib = build_host(model)
+    lib.kmc_host_use_items(1 if items else 0)
     st = np.zeros(320, dtype=np.uint64)
     buf = None
     cap = 0

@@ -233,3 +233,14 @@ def test_two_gpu_sharded_run_matches_golden(goldens):
     g = goldens["kip320_3x4_r4e2"]
     assert r["config"]["distinct"] == g["distinct"] and r["config"]["generated"] == g["generated"]
     assert sum(r["config"]["per_rank_distinct"]) == g["distinct"]
+
+
+def test_candidate_overflow_is_an_error_not_a_wrong_answer():
+    """Chunks are sized for a realistic fan-out; if a model exceeds it the run fails loudly (KMC_E_CAND_FULL)."""
+    from kafka_specification_b200.runtime import KmcError
+    with checker("frl_3x4x2", cand_bytes=1 << 20, fanout_bound=1) as ck:
+        with pytest.raises(KmcError) as e:
+            ck.run()
+        assert e.value.code == -10
+    with checker("frl_3x4x2", cand_bytes=1 << 20, fanout_bound=32) as ck:
+        assert ck.run().distinct == 29791

@@ -110,3 +110,14 @@ def test_false_assume_is_rejected():
     with pytest.raises(LowerError):              # AsyncIsr.tla:27-29: MaxOffset > 0
         lower_model("MCAsyncIsr", DIRS, open(os.path.join(ROOT, "models", "MCAsyncIsr.cfg")).read().replace(
             "MaxOffset = 2", "MaxOffset = 0"))
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["frl_tiny", "kip320_n2", "kip279_n2", "firsttry_n2", "asyncisr_v2", "kip320_small"])
+def test_two_phase_item_form_equals_expand(name, goldens, registry):
+    """item_guard/item_body (what the CUDA expand kernel runs) enumerate exactly expand()'s successors."""
+    g = goldens[name]
+    m = _lower(registry, name)
+    r = run_host(m, max_states=3_000_000, items=True)
+    for k in ("distinct", "generated", "depth", "levels", "deadlocks"):
+        assert r[k] == g[k], k
