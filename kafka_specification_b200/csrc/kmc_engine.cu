@@ -77,6 +77,18 @@ __host__ __device__ __forceinline__ uint64_t fingerprint(const State& s) {
   return h ? h : 1;
 }
 
+// Identity of a state in the set (and its owner rank): with SYMMETRY it is the fingerprint of the
+// orbit representative (smallest packed image under the symmetry group, TLC's symmetry reduction);
+// the state that is stored, expanded and shown in traces stays the one that was actually reached.
+__host__ __device__ __forceinline__ uint64_t state_fp(const State& s) {
+  if (M::HAS_SYMMETRY) {
+    State c;
+    M::canonicalize(s, c);
+    return fingerprint(c);
+  }
+  return fingerprint(s);
+}
+
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t fp, uint32_t world) {
   return (uint32_t)(((fp >> 32) * (uint64_t)world) >> 32);
 }
@@ -215,7 +227,7 @@ __device__ __forceinline__ Prefetched prefetch_row(const Params& p, const State&
   f.inmodel = false;
   if (valid) {
     f.inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
-    f.fp = fingerprint(s);
+    f.fp = state_fp(s);
     if (f.inmodel) {
       const uint64_t* base = p.table + (bucket_of(f.fp, p.bucket_mask) << 2);
       f.lo = ld_bucket_half(base);
@@ -281,7 +293,7 @@ __device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t*
 #pragma unroll
   for (int i = 0; i < W; ++i) s.w[i] = words[i];
   uint32_t dest = 0xFFu;
-  if (valid) dest = MULTI ? owner_of(fingerprint(s), p.world) : 0u;
+  if (valid) dest = MULTI ? owner_of(state_fp(s), p.world) : 0u;
   unsigned peers = __match_any_sync(0xffffffffu, dest);
   unsigned lane = lane_id();
   int leader = __ffs(peers) - 1;
@@ -376,7 +388,7 @@ struct CandSink {
       row[W] = meta;
     } else {
       // staging area full (rare burst): straight to global memory, one claim per lane group
-      uint32_t dest = MULTI ? owner_of(fingerprint(s), p.world) : 0u;
+      uint32_t dest = MULTI ? owner_of(state_fp(s), p.world) : 0u;
       unsigned long long gpos = atomicAdd(&p.ctr->cand_count[dest], 1ull);
       if (gpos >= p.region_rows) {
         failed = KMC_FAIL_CAND_FULL;
@@ -1006,7 +1018,7 @@ static int seed_init(Engine& E) {
   for (int i = 0; i < M::NUM_INIT; ++i) {
     State s;
     memcpy(s.w, M::INIT_STATES[i], sizeof(s.w));
-    uint32_t d = E.world > 1 ? owner_of(fingerprint(s), E.world) : 0;
+    uint32_t d = E.world > 1 ? owner_of(state_fp(s), E.world) : 0;
     // every rank seeds the same init states but only rank 0 contributes them, so that the
     // generated count and the exchange see each init state exactly once
     if (E.rank != 0) continue;

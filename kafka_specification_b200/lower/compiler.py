@@ -758,6 +758,13 @@ class Lowerer:
         if k in ("app", "inst"):
             op = self.find_operator(e, ctx, fm, env)
             if op is None:
+                if k == "app" and e[1] == "Permutations" and len(e[2]) == 1:
+                    # TLC module: all permutations of a constant finite set (used by SYMMETRY)
+                    base = self.ev(e[2][0], ctx, fm, env, S)
+                    if not isinstance(base, frozenset):
+                        raise LowerError("Permutations of a non-constant set")
+                    elems = sorted(base, key=sort_key)
+                    return frozenset(FnVal(dict(zip(elems, p))) for p in itertools.permutations(elems))
                 raise LowerError(f"unknown operator {e[1]}")
             target, defctx, args = op
             if not isinstance(target, Closure) and not target.params:
@@ -1339,6 +1346,83 @@ class Lowerer:
             self.cg.close()
             self.cg.emit("else sink.fail(KMC_FAIL_LAYOUT);")
         self.cg.close()
+
+    # ------------------------------------------------------------ symmetry
+    def permute_const(self, v, pmap: dict):
+        if is_atom_const(v):
+            return pmap.get(v, v)
+        if isinstance(v, frozenset):
+            return frozenset(self.permute_const(x, pmap) for x in v)
+        if isinstance(v, FnVal):
+            return FnVal({self.permute_const(k, pmap): self.permute_const(x, pmap) for k, x in v.items})
+        if isinstance(v, tuple):
+            return tuple(self.permute_const(x, pmap) for x in v)
+        return v
+
+    def permute_sval(self, v, pmap: dict):
+        """Image of a (symbolic) value under a permutation of model values; returns ``v`` itself
+        when nothing in it can move, so that unchanged variables are not re-encoded."""
+        if is_const(v):
+            return self.permute_const(v, pmap)
+        if isinstance(v, (SInt, SBool)):
+            return v
+        if isinstance(v, SAtom):
+            moved = [a for a in v.uni if pmap.get(a, a) != a]
+            if not moved:
+                return v
+            e = v.s
+            for a in moved:
+                e = f"({v.s} == {self.gid(a)} ? {self.gid(pmap[a])} : {e})"
+            return SAtom(self.tmp_int(e), tuple(dict.fromkeys(pmap.get(a, a) for a in v.uni)))
+        if isinstance(v, SRec):
+            new = {f: self.permute_sval(x, pmap) for f, x in v.fields.items()}
+            return v if all(new[f] is v.fields[f] for f in new) else SRec(new)
+        if isinstance(v, SFn):
+            keys = [self.permute_const(k, pmap) for k in v.keys]
+            vals = [self.permute_sval(x, pmap) for x in v.vals]
+            if keys == list(v.keys) and all(a is b for a, b in zip(vals, v.vals)):
+                return v
+            order = sorted(range(len(keys)), key=lambda i: sort_key(keys[i]))
+            return SFn([keys[i] for i in order], [vals[i] for i in order])
+        if isinstance(v, SSet):
+            items = [(g, self.permute_sval(x, pmap)) for g, x in v.items]
+            if all(a[1] is b[1] for a, b in zip(items, v.items)):
+                return v
+            return SSet(items, distinct=v.distinct)
+        if isinstance(v, SUnion):
+            alts = [(g, self.permute_sval(x, pmap)) for g, x in v.alts]
+            return v if all(a[1] is b[1] for a, b in zip(alts, v.alts)) else SUnion(alts)
+        raise LowerError(f"cannot permute {v!r}")
+
+    def gen_permuted_words(self, pmap: dict) -> list[str]:
+        """C expressions of the packed words of the current state's image under ``pmap``."""
+        lay = self.layout
+        out: dict[int, str] = {}
+        self.traps = []
+        for v in self.variables:
+            ty = lay.var_types[v]
+            img = self.permute_sval(self.cur[v], pmap)
+            if img is self.cur[v]:
+                continue
+            ty.write(self, img, out)
+        self.traps = []          # a permuted reachable value always fits its own layout
+        by_word: dict[int, list] = {}
+        for idx, code in out.items():
+            a = lay.atoms[idx]
+            by_word.setdefault(a.word, []).append((a, code))
+        words = []
+        for w in range(lay.words):
+            lst = by_word.get(w, [])
+            if not lst:
+                words.append(f"s.w[{w}]")
+                continue
+            mask = 0
+            parts = []
+            for a, code in lst:
+                mask |= a.mask << a.shift
+                parts.append(f"((uint64_t)({code}) << {a.shift})" if a.shift else f"(uint64_t)({code})")
+            words.append(f"((s.w[{w}] & ~0x{mask:x}ull) | " + " | ".join(parts) + ")")
+        return words
 
     # ------------------------------------------------------------ predicates
     def named_def(self, name: str) -> tuple[Def, ModuleContext]:

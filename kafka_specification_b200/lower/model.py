@@ -447,8 +447,8 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     cfg = parse_cfg(cfg_text)
     root = load_root(module, search_dirs)
     lw = Lowerer(root, cfg)
-    if cfg.symmetry or cfg.view or cfg.properties or cfg.action_constraints:
-        raise LowerError("SYMMETRY / VIEW / PROPERTY / ACTION_CONSTRAINT are not supported")
+    if cfg.view or cfg.properties or cfg.action_constraints:
+        raise LowerError("VIEW / PROPERTY / ACTION_CONSTRAINT are not supported")
 
     # ASSUMEs of the root module (TLC evaluates them once at start-up)
     for a, mod in root.assumes:
@@ -540,8 +540,31 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     con_lines = list(lw.prologue) + list(lw.cg.lines)
     con_lines.append(f"  return {lw.bstr(c_all)};")
 
+    # SYMMETRY: canonicalize(s) = lexicographically smallest packed image of s under the symmetry group
+    sym_lines: list[str] = []
+    n_perms = 0
+    if cfg.symmetry:
+        sdf, sctx = lw.named_def(cfg.symmetry)
+        pv = lw.ev(sdf.body, sctx, sdf.module, {}, None)
+        if not isinstance(pv, frozenset) or not all(isinstance(f, FnVal) for f in pv):
+            raise LowerError("SYMMETRY must name a constant set of permutations (e.g. Permutations(Replicas))")
+        lw.begin_function()
+        for f in sorted(pv, key=sort_key):
+            pmap = {k: x for k, x in f.items if k != x}
+            if not pmap:
+                continue
+            n_perms += 1
+            lw.cg.open()
+            words = lw.gen_permuted_words(pmap)
+            lw.cg.emit("State c;")
+            for w, e in enumerate(words):
+                lw.cg.emit(f"c.w[{w}] = {e};")
+            lw.cg.emit("if (state_less(c, best)) best = c;")
+            lw.cg.close()
+        sym_lines = list(lw.prologue) + list(lw.cg.lines)
+
     name = name or module
-    body_digest = hashlib.sha256(("\n".join(expand_lines + inv_lines + con_lines) + cfg_text).encode()).hexdigest()[:16]
+    body_digest = hashlib.sha256(("\n".join(expand_lines + inv_lines + con_lines + sym_lines) + cfg_text).encode()).hexdigest()[:16]
     unpack = lw.unpack_lines()
 
     parts = [HEADER_PROLOGUE.format(
@@ -616,6 +639,18 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     parts.append("KMC_HD bool in_model(const State& s) {")
     parts.extend(unpack)
     parts.extend(con_lines)
+    parts.append("}")
+    parts.append(f"/* SYMMETRY: {n_perms} non-identity permutations; canonicalize = smallest packed image (identity if none) */")
+    parts.append(f"static constexpr bool HAS_SYMMETRY = {'true' if n_perms else 'false'};")
+    parts.append("KMC_HD bool state_less(const State& a, const State& b) {")
+    parts.append("  for (int i = W - 1; i >= 0; --i) { if (a.w[i] != b.w[i]) return a.w[i] < b.w[i]; }")
+    parts.append("  return false;")
+    parts.append("}")
+    parts.append("KMC_HD void canonicalize(const State& s, State& best) {")
+    parts.append("  best = s;")
+    if n_perms:
+        parts.extend(unpack)
+        parts.extend(sym_lines)
     parts.append("}")
     parts.append("}  // namespace kmc_model")
     header = "\n".join(parts) + "\n"

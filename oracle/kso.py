@@ -41,13 +41,15 @@ def lib():
         _lib.kso_run.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint64,
                                  ctypes.c_uint, ctypes.POINTER(Result), ctypes.c_void_p, ctypes.c_uint64]
         _lib.kso_run.restype = ctypes.c_int
+        _lib.kso_run_sym.argtypes = _lib.kso_run.argtypes + [ctypes.c_int]
+        _lib.kso_run_sym.restype = ctypes.c_int
         _lib.kso_state_size.argtypes = [ctypes.c_int]
         _lib.kso_state_size.restype = ctypes.c_size_t
     return _lib
 
 
 def run(model: str, params: list[int], threads: int = 0, max_states: int = 0, invariants: list[str] | None = None,
-        dump: bool = False) -> dict:
+        dump: bool = False, symmetry: bool = False) -> dict:
     """params: Kafka family [n, L, R, E]; frl [n, L, R]; idsequence [MaxId]; asyncisr [n, MaxOffset, MaxVersion]."""
     threads = threads or os.cpu_count() or 1
     mask = 0
@@ -61,8 +63,8 @@ def run(model: str, params: list[int], threads: int = 0, max_states: int = 0, in
     if dump:
         cap = max_states or (1 << 22)
         buf = np.zeros(cap * lib().kso_state_size(MODELS[model]), dtype=np.uint8)
-    rc = lib().kso_run(MODELS[model], arr, threads, max_states, mask, ctypes.byref(res),
-                       buf.ctypes.data if dump else None, cap)
+    rc = lib().kso_run_sym(MODELS[model], arr, threads, max_states, mask, ctypes.byref(res),
+                           buf.ctypes.data if dump else None, cap, 1 if symmetry else 0)
     if rc != 0:
         raise RuntimeError(f"kso_run failed: {rc}")
     depth = int(res.depth)

@@ -663,6 +663,64 @@ static int leader_in_isr(const KState* s) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * SYMMETRY Permutations(Replicas) (TLC's symmetry reduction; models/MCKip320Sym.tla).  Replicas are
+ * used only through equality and membership (KafkaReplication.tla:126-131,158-179), so permuting them
+ * maps reachable states to reachable states.  The orbit representative is the permuted image with
+ * the smallest byte string.
+ * ---------------------------------------------------------------------------------------- */
+static inline uint8_t perm_bits(uint8_t m, const int* pi, int n) {
+  uint8_t o = 0;
+  for (int r = 0; r < n; ++r) if ((m >> r) & 1) o |= (uint8_t)(1u << pi[r]);
+  return o;
+}
+static void kafka_permute(const Cfg* c, const KState* s, const int* pi, KState* t) {
+  memset(t, 0, sizeof(*t));
+  for (int r = 0; r < c->n; ++r) {
+    int q = pi[r];
+    t->end[q] = s->end[r];
+    memcpy(t->rec_id[q], s->rec_id[r], LMAX);
+    memcpy(t->rec_ep[q], s->rec_ep[r], LMAX);
+    t->hw[q] = s->hw[r];
+    t->rs_epoch[q] = s->rs_epoch[r];
+    t->rs_leader[q] = s->rs_leader[r] == NONE ? NONE : (uint8_t)pi[s->rs_leader[r]];
+    t->rs_isr[q] = perm_bits(s->rs_isr[r], pi, c->n);
+  }
+  t->next_record_id = s->next_record_id;
+  t->next_leader_epoch = s->next_leader_epoch;
+  t->q_epoch = s->q_epoch;
+  t->q_leader = s->q_leader == NONE ? NONE : (uint8_t)pi[s->q_leader];
+  t->q_isr = perm_bits(s->q_isr, pi, c->n);
+  for (int i = 0; i < s->nreq; ++i) {
+    Req q;
+    memset(&q, 0, sizeof(q));
+    q.epoch = s->req[i].epoch;
+    q.leader = s->req[i].leader == NONE ? NONE : (uint8_t)pi[s->req[i].leader];
+    q.isr = perm_bits(s->req[i].isr, pi, c->n);
+    req_insert(t, q);
+  }
+}
+static int next_perm(int* a, int n) {          /* lexicographic next permutation */
+  int i = n - 2;
+  while (i >= 0 && a[i] > a[i + 1]) --i;
+  if (i < 0) return 0;
+  int j = n - 1;
+  while (a[j] < a[i]) --j;
+  int x = a[i]; a[i] = a[j]; a[j] = x;
+  for (int l = i + 1, r = n - 1; l < r; ++l, --r) { x = a[l]; a[l] = a[r]; a[r] = x; }
+  return 1;
+}
+static void kafka_canonicalize(const Cfg* c, KState* s) {
+  int pi[NMAX];
+  for (int r = 0; r < c->n; ++r) pi[r] = r;
+  KState best = *s, t;
+  while (next_perm(pi, c->n)) {
+    kafka_permute(c, s, pi, &t);
+    if (memcmp(&t, &best, sizeof(KState)) < 0) best = t;
+  }
+  *s = best;
+}
+
+/* ------------------------------------------------------------------------------------------
  * AsyncIsr.tla (+ the Bound constraint of models/MCAsyncIsr.tla); Leader = replica 0
  * ---------------------------------------------------------------------------------------- */
 static inline int msg_bit(const Cfg* c, int isr, int ver) { return ver * (1 << c->n) + isr; }
@@ -826,6 +884,7 @@ typedef struct {
   uint64_t table_mask;
   uint8_t* dead;             /* 1: slot allocated by a loser of an insertion race (hole) */
   unsigned want_inv;
+  int symmetry;
   uint64_t stop_at;
   /* per level */
   uint64_t lvl_first, lvl_end, level;
@@ -911,7 +970,8 @@ static void* worker(void* arg) {
       gen += out.n;
       if (out.n == 0) ++dead;
       for (int k = 0; k < out.n; ++k) {
-        const uint8_t* t = out.buf + (size_t)k * sz;
+        uint8_t* t = out.buf + (size_t)k * sz;
+        if (b->symmetry) kafka_canonicalize(c, (KState*)t);
         if (!in_model(c, t)) {
           ++oom;
           unsigned v = b->want_inv ? violated(c, t, b->want_inv) : 0;
@@ -944,9 +1004,20 @@ static size_t state_size(int model) {
 /* params: Kafka family {n, L, R, E}; FRL {n, L, R}; IdSequence {MaxId}; AsyncIsr {n, MaxOffset, MaxVersion}.
  * inv_mask: bit i = evaluate invariant i on every new state (statistics only; the search never stops).
  * dump: optional buffer receiving all distinct state records (dump_cap records).                    */
+int kso_run_sym(int model, const int* params, int threads, uint64_t max_states, unsigned inv_mask, kso_result* res,
+                uint8_t* dump, uint64_t dump_cap, int symmetry);
+
 int kso_run(int model, const int* params, int threads, uint64_t max_states, unsigned inv_mask, kso_result* res,
             uint8_t* dump, uint64_t dump_cap) {
+  return kso_run_sym(model, params, threads, max_states, inv_mask, res, dump, dump_cap, 0);
+}
+
+/* symmetry != 0: SYMMETRY Permutations(Replicas) (Kafka family only) */
+int kso_run_sym(int model, const int* params, int threads, uint64_t max_states, unsigned inv_mask, kso_result* res,
+                uint8_t* dump, uint64_t dump_cap, int symmetry) {
+  if (symmetry && !(model >= M_TRUNCHW && model <= M_FIRSTTRY)) return -3;
   Bfs* b = calloc(1, sizeof(Bfs));
+  b->symmetry = symmetry;
   Cfg* c = &b->cfg;
   c->model = model;
   c->ssize = state_size(model);
@@ -982,6 +1053,7 @@ int kso_run(int model, const int* params, int threads, uint64_t max_states, unsi
 
   uint8_t* init = calloc(1, c->ssize);
   init_state(c, init);
+  if (symmetry) kafka_canonicalize(c, (KState*)init);
   atomic_store(&b->generated, 1);
   if (in_model(c, init)) insert_state(b, init);
   unsigned v0 = inv_mask ? violated(c, init, inv_mask) : 0;

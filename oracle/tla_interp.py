@@ -348,6 +348,10 @@ class Interp:
         if k == "app" or k == "inst":
             op = self.find_operator(e, ctx, fm, env)
             if op is None:
+                if k == "app" and e[1] == "Permutations" and len(e[2]) == 1:
+                    # TLC module: the set of all permutations (bijections S -> S) of a finite set
+                    elems = sorted(set_elems(self.ev(e[2][0], ctx, fm, env, st, st1)), key=sort_key)
+                    return frozenset(FnVal(dict(zip(elems, p))) for p in itertools.permutations(elems))
                 raise EvalError(f"unknown operator {e[1]}")
             target, defctx, args = op
             if k == "inst" and not target.params:
@@ -768,6 +772,19 @@ def resolve_init_next(root: ModuleContext, cfg: Config):
     raise EvalError("cfg needs INIT+NEXT or SPECIFICATION")
 
 
+def permute_value(v, mapping: dict):
+    """Applies a permutation of model values to a TLA+ value (TLC's SYMMETRY semantics)."""
+    if isinstance(v, ModelValue):
+        return mapping.get(v, v)
+    if isinstance(v, frozenset):
+        return frozenset(permute_value(x, mapping) for x in v)
+    if isinstance(v, FnVal):
+        return FnVal({permute_value(k, mapping): permute_value(x, mapping) for k, x in v.items})
+    if isinstance(v, tuple):
+        return tuple(permute_value(x, mapping) for x in v)
+    return v
+
+
 def state_text(variables, st: dict) -> str:
     return "\n".join(f"/\\ {v} = {fmt(st[v])}" for v in variables)
 
@@ -782,8 +799,23 @@ def run_bfs(module: str, search_dirs: list[str], cfg_text: str, max_states: int 
     init_e, next_e = resolve_init_next(root, cfg)
     variables = it.variables
 
+    perms = []
+    if cfg.symmetry:
+        pv = it.ev(("id", cfg.symmetry), root, None, {}, None, None)
+        perms = [dict(f.items) for f in set_elems(pv)]
+
     def key(st):
-        return tuple(st[v] for v in variables)
+        k = tuple(st[v] for v in variables)
+        if not perms:
+            return k
+        # orbit representative: the permuted image with the smallest canonical text
+        best, best_text = None, None
+        for m in perms:
+            kk = tuple(permute_value(x, m) for x in k)
+            t = "|".join(fmt(x) for x in kk)
+            if best_text is None or t < best_text:
+                best, best_text = kk, t
+        return best
 
     def in_model(st):
         return all(it.eval_named_predicate(c, st) for c in cfg.constraints)

@@ -60,8 +60,9 @@ def main():
         cfg = parse_cfg(cfg_text)
         model, params = spec["kso"]
         t0 = time.time()
-        b = kso.run(model, params, max_states=spec.get("max_states", 4_000_000), invariants=cfg.invariants)
-        g = {"module": spec["module"], "cfg": spec["cfg"], "kso": spec["kso"],
+        b = kso.run(model, params, max_states=spec.get("max_states", 4_000_000), invariants=cfg.invariants,
+                    symmetry=bool(spec.get("symmetry")))
+        g = {"module": spec["module"], "cfg": spec["cfg"], "kso": spec["kso"], "symmetry": bool(spec.get("symmetry")),
              "distinct": b["distinct"], "generated": b["generated"], "depth": b["depth"], "levels": b["levels"],
              "deadlocks": b["deadlocks"], "first_violation_level": b["first_violation_level"],
              "check_deadlock": cfg.check_deadlock, "sources": ["oracle_b"]}
@@ -80,7 +81,8 @@ def main():
             for inv, lvl in b["first_violation_level"].items():
                 assert a["first_violation_level"][inv] == lvl, (name, inv, a["first_violation_level"], lvl)
             g["first_violation_level"] = a["first_violation_level"]     # includes TypeOk
-            g["state_digest"] = state_digest(a["states"])
+            if not spec.get("symmetry"):       # under SYMMETRY the choice of orbit representatives is free
+                g["state_digest"] = state_digest(a["states"])
             g["sources"].append("oracle_a")
         out[name] = g
         print(f"{name}: distinct={g['distinct']} generated={g['generated']} depth={g['depth']} "

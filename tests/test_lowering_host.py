@@ -16,8 +16,8 @@ from hostmodel import lower_model, run_host
 DIRS = [REFERENCE, os.path.join(ROOT, "models")]
 
 SMALL = ["idsequence", "frl_tiny", "frl_3x4x2", "kip320_n2", "trunchw_n2", "kip101_n2", "kip279_n2", "firsttry_n2",
-         "asyncisr_v2", "asyncisr_small"]
-MEDIUM = ["kip320_small", "trunchw_small", "kip101_small", "kip279_small", "firsttry_small"]
+         "asyncisr_v2", "asyncisr_small", "kip320sym_n2"]
+MEDIUM = ["kip320_small", "trunchw_small", "kip101_small", "kip279_small", "firsttry_small", "kip320sym_small"]
 
 
 def _lower(registry, name):
@@ -121,3 +121,15 @@ def test_two_phase_item_form_equals_expand(name, goldens, registry):
     r = run_host(m, max_states=3_000_000, items=True)
     for k in ("distinct", "generated", "depth", "levels", "deadlocks"):
         assert r[k] == g[k], k
+
+
+@needs_reference
+def test_symmetry_reduction_counts_orbits(goldens, registry):
+    """SYMMETRY Permutations(Replicas): the set holds one representative per orbit; the orbit count
+    lies between |states| / n! and |states|, and every count equals both oracles'."""
+    full, sym = goldens["kip320_small"], goldens["kip320sym_small"]
+    assert full["distinct"] / 6 <= sym["distinct"] < full["distinct"]
+    assert sym["depth"] == full["depth"]
+    m = _lower(registry, "kip320sym_small")
+    r = run_host(m, max_states=1_000_000)
+    assert (r["distinct"], r["generated"], r["levels"]) == (sym["distinct"], sym["generated"], sym["levels"])

@@ -25,7 +25,7 @@ def test_oracle_b_matches_goldens(goldens):
             continue                      # the headline configs take minutes and tens of GB on the CPU
         model, params = g["kso"]
         invs = [i for i in g["first_violation_level"] if i != "TypeOk"]
-        r = kso.run(model, params, max_states=4_000_000, invariants=invs)
+        r = kso.run(model, params, max_states=4_000_000, invariants=invs, symmetry=bool(g.get("symmetry")))
         for k in ("distinct", "generated", "depth", "levels", "deadlocks"):
             assert r[k] == g[k], (name, k)
         for inv in invs:
