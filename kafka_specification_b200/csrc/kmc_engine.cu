@@ -282,8 +282,8 @@ __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint
 // per flush (instead of one ~600-cycle atomic round trip per emit site), coalesced row stores,
 // and -- multi-rank -- the owner computation (a fingerprint) done with all 32 lanes busy instead
 // of inside the divergent emit site.
-static constexpr int STAGE_ROWS = 96;      // rows per warp
-static constexpr int STAGE_FLUSH = 48;     // flush once at least this many rows are staged
+static constexpr int STAGE_ROWS = (ROW <= 5) ? 96 : (ROW <= 8 ? 64 : 40);   // rows per warp (<= 200 KB per 1024-thread CTA)
+static constexpr int STAGE_FLUSH = STAGE_ROWS / 2;                          // flush once at least this many rows are staged
 
 template <bool MULTI>
 __device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t* words, uint64_t meta, bool valid,
@@ -924,6 +924,13 @@ static int grid_for(const Engine& E, uint64_t n, int block, int per_sm) {
   return (int)g;
 }
 
+static size_t expand_smem_bytes() {
+  return (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
+}
+static size_t expand2_smem_bytes() {
+  return expand_smem_bytes() + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4;
+}
+
 static int engine_alloc(Engine& E) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -967,6 +974,14 @@ static int engine_alloc(Engine& E) {
   if (E.world > 1) {
     E.recv_rows = E.region_rows * E.world;
     CK(cudaMalloc(&E.recv, E.recv_rows * ROW * 8));
+  }
+  // the expand kernels stage successor rows in > 48 KB of dynamic shared memory
+  CK(cudaFuncSetAttribute(k_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
+  if (E.two_phase) {
+    CK(cudaFuncSetAttribute(k_expand2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand2_smem_bytes()));
+    CK(cudaFuncSetAttribute(k_expand2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand2_smem_bytes()));
   }
   CK(cudaMalloc(&E.ctr, sizeof(DevCounters)));
   CK(cudaMalloc(&E.viol_ring, (size_t)VIOL_RING * VIOL_ROW * 8));
@@ -1066,24 +1081,11 @@ static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool fused =
   while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
   uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
   int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
-  const size_t smem = (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = expand_smem_bytes();
   grid *= EXPAND_MIN_BLOCKS;
   if ((uint64_t)grid > tiles) grid = (int)std::max<uint64_t>(tiles, 1);
   if (E.two_phase && !fused) {
-    const size_t smem2 = smem + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4;
-    static bool attr2 = false;
-    if (!attr2) {
-      CK(cudaFuncSetAttribute(k_expand2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      CK(cudaFuncSetAttribute(k_expand2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      attr2 = true;
-    }
+    const size_t smem2 = expand2_smem_bytes();
     TimedLaunch t(E, 0);
     if (E.world > 1) k_expand2<true><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);
     else k_expand2<false><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);

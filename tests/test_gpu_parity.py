@@ -188,7 +188,8 @@ def _assert_trace_is_behaviour(name, trace, ck):
 
 
 @pytest.mark.parametrize("name,opts", [("kip320_3x4_r4e2", {"table_log2": 26, "max_states": 20_000_000}),
-                                       ("kip320_3x4_r3e3", {"table_log2": 28, "max_states": 70_000_000})])
+                                       ("kip320_3x4_r3e3", {"table_log2": 28, "max_states": 70_000_000}),
+                                       ("kip320sym_3x4_r4e3", {"table_log2": 28, "max_states": 60_000_000})])
 def test_headline_sizes_match_oracle_b_golden(name, opts, goldens):
     """Full-size runs (10^7..10^8 states): counts and per-level widths against the committed Oracle B golden."""
     g = goldens[name]
