@@ -463,31 +463,31 @@ struct GroupRunner<M::NUM_GROUPS, MULTI, FUSED> {
 //      successor construction runs with (almost) all lanes on (almost) the same code.
 // ----------------------------------------------------------------------------------------
 static constexpr int LIST_CAP = 16384;
+static constexpr int MAX_GROUP_ITEMS = 64;
 
 struct TwoPhaseCtx {
   uint64_t first, tile_base, count;
   int spt;
   uint64_t* wbuf;
   unsigned* wcnt;
-  unsigned* list;        // [LIST_CAP]
+  unsigned* list;        // [LIST_CAP] entries: item-in-group << 16 | state slot in the tile
   unsigned* list_count;
   unsigned* succ;        // successors per tile state [EXPAND_BLOCK * EXPAND_SPT]
+  unsigned* item_cnt;    // [MAX_GROUP_ITEMS] enabled pairs per item, then running cursor
+  unsigned* item_off;    // [MAX_GROUP_ITEMS] start of each item's segment in the list
 };
 
-// Each item body is its own (non-inlined) function: inlining all bodies of a group into the
-// dispatch chain lets the compiler hoist every body's unpacking above the chain, which blows the
-// 64-register budget of a 1024-thread CTA (2 KB of spills measured).
-template <int I, class Sink>
-__device__ __noinline__ void item_body_call(const State& s, Sink& sink) {
-  M::item_body(M::ItemTag<I>{}, s, sink);
-}
-
+// Bodies are inlined into an if-chain; the opaque copy stops the compiler from hoisting every
+// body's unpacking above the chain (which overflows the 64-register budget of a 1024-thread CTA).
 template <int I, int END>
 struct ItemDispatch {
   template <class Sink>
   static __device__ __forceinline__ void run(int item, const State& s, Sink& sink) {
     if (item == I) {
-      item_body_call<I, Sink>(s, sink);
+      State t = s;
+#pragma unroll
+      for (int k = 0; k < W; ++k) asm volatile("" : "+l"(t.w[k]));
+      M::item_body(M::ItemTag<I>{}, t, sink);
       return;
     }
     ItemDispatch<I + 1, END>::run(item, s, sink);
@@ -499,77 +499,104 @@ struct ItemDispatch<END, END> {
   static __device__ __forceinline__ void run(int, const State&, Sink&) {}
 };
 
-template <int I, int END, int BEGIN, bool MULTI>
-struct ItemGuards {
-  static __device__ __forceinline__ void run(const Params& p, const TwoPhaseCtx& c, int& failed) {
-    const unsigned lane = lane_id();
-#pragma unroll 1
-    for (int j = 0; j < c.spt; ++j) {
-      const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
-      const uint64_t i = c.tile_base + loc;
-      bool en = false;
-      State s;
-      if (i < c.count) {
-        load_state(s, p.store + (c.first + i) * W);
-        en = M::item_guard(M::ItemTag<I>{}, s);
-      }
-      unsigned mask = __ballot_sync(0xffffffffu, en);
-      if (mask) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(c.list_count, (unsigned)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (en) {
-          unsigned pos = base + __popc(mask & ((1u << lane) - 1));
-          if (pos < (unsigned)LIST_CAP) {
-            c.list[pos] = ((unsigned)(I - BEGIN) << 16) | loc;
-          } else {
-            // list full (a group in which nearly everything is enabled): run the body right here
-            CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
-            item_body_call<I, CandSink<MULTI>>(s, sink);
-            if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
-            failed |= sink.failed;
-          }
-        }
-      }
-    }
-    ItemGuards<I + 1, END, BEGIN, MULTI>::run(p, c, failed);
-  }
-};
-template <int END, int BEGIN, bool MULTI>
-struct ItemGuards<END, END, BEGIN, MULTI> {
-  static __device__ __forceinline__ void run(const Params&, const TwoPhaseCtx&, int&) {}
-};
-
 template <int G, bool MULTI>
 struct GroupRunner2 {
   static __device__ __forceinline__ void run(const Params& p, const TwoPhaseCtx& c, int& failed, ExpandStats& xs) {
     constexpr int BEGIN = M::GROUP_ITEM_BEGIN[G];
     constexpr int END = M::GROUP_ITEM_BEGIN[G + 1];
-    __syncthreads();                                   // previous group's list fully consumed and reset
-    ItemGuards<BEGIN, END, BEGIN, MULTI>::run(p, c, failed);
-    __syncthreads();                                   // list complete
-    unsigned total = *c.list_count;
-    if (total > (unsigned)LIST_CAP) total = LIST_CAP;
+    constexpr int NI = END - BEGIN;
+    static_assert(NI <= MAX_GROUP_ITEMS, "too many items in one group");
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (unsigned e0 = warp * 32; e0 < total; e0 += EXPAND_BLOCK) {
-      const unsigned e = e0 + lane;
-      if (e < total) {
-        const unsigned entry = c.list[e];
-        const unsigned loc = entry & 0xFFFFu;
-        const uint64_t i = c.tile_base + loc;
-        State s;
-        load_state(s, p.store + (c.first + i) * W);
-        CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
-        ItemDispatch<BEGIN, END>::run((int)(entry >> 16) + BEGIN, s, sink);
-        if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
-        failed |= sink.failed;
+    // ---- phase A1: guard masks (one unpack per state and group), count enabled pairs per item
+    uint64_t masks[EXPAND_SPT];
+#pragma unroll
+    for (int j = 0; j < EXPAND_SPT; ++j) {
+      masks[j] = 0;
+      if (j < c.spt) {
+        const uint64_t i = c.tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
+        if (i < c.count) {
+          State s;
+          load_state(s, p.store + (c.first + i) * W);
+          masks[j] = M::group_guard_mask(M::GroupTag<G>{}, s);
+        }
       }
-      flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
+    }
+#pragma unroll 1
+    for (int k = 0; k < NI; ++k) {
+      unsigned n = 0;
+#pragma unroll
+      for (int j = 0; j < EXPAND_SPT; ++j) n += __popc(__ballot_sync(0xffffffffu, (masks[j] >> k) & 1));
+      if (lane == 0 && n) atomicAdd(&c.item_cnt[k], n);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *c.list_count = 0;
+    // ---- exclusive prefix over the (few) items
+    if (threadIdx.x == 0) {
+      unsigned run_total = 0;
+      for (int k = 0; k < NI; ++k) {
+        unsigned n = c.item_cnt[k];
+        c.item_off[k] = run_total;
+        c.item_cnt[k] = 0;               // becomes the running cursor of phase A2
+        run_total += n;
+      }
+      *c.list_count = run_total;
+    }
+    __syncthreads();
+    const unsigned total = *c.list_count;
+    if (total > (unsigned)LIST_CAP) {
+      // more enabled pairs than the list holds (a group in which nearly everything is enabled):
+      // run this group in one phase, every lane on its own states
+#pragma unroll 1
+      for (int j = 0; j < c.spt; ++j) {
+        const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
+        const uint64_t i = c.tile_base + loc;
+        if (i < c.count) {
+          State s;
+          load_state(s, p.store + (c.first + i) * W);
+          CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
+          M::expand_group(M::GroupTag<G>{}, s, sink);
+          if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
+          failed |= sink.failed;
+        }
+        flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
+      }
+    } else {
+      // ---- phase A2: scatter (item, state) pairs into per-item segments of the list
+#pragma unroll 1
+      for (int k = 0; k < NI; ++k) {
+#pragma unroll
+        for (int j = 0; j < EXPAND_SPT; ++j) {
+          const bool en = (masks[j] >> k) & 1;
+          const unsigned m = __ballot_sync(0xffffffffu, en);
+          if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&c.item_cnt[k], (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (en) c.list[c.item_off[k] + base + __popc(m & ((1u << lane) - 1))] = ((unsigned)k << 16) | ((unsigned)j * EXPAND_BLOCK + threadIdx.x);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase B: bodies, 32 list entries at a time (entries of one item are contiguous)
+#pragma unroll 1
+      for (unsigned e0 = warp * 32; e0 < total; e0 += EXPAND_BLOCK) {
+        const unsigned e = e0 + lane;
+        if (e < total) {
+          const unsigned entry = c.list[e];
+          const unsigned loc = entry & 0xFFFFu;
+          const uint64_t i = c.tile_base + loc;
+          State s;
+          load_state(s, p.store + (c.first + i) * W);
+          CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
+          ItemDispatch<BEGIN, END>::run((int)(entry >> 16) + BEGIN, s, sink);
+          if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
+          failed |= sink.failed;
+        }
+        flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
+      }
+    }
+    if (threadIdx.x < NI) c.item_cnt[threadIdx.x] = 0;
+    __syncthreads();                                   // list consumed before the next group refills it
     GroupRunner2<G + 1, MULTI>::run(p, c, failed, xs);
   }
 };
@@ -589,8 +616,12 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand2(Params p, uint64_t 
   unsigned* list_count = u + NW;
   unsigned* list = u + NW + 4;
   unsigned* succ = list + LIST_CAP;
+  unsigned* item_cnt = succ + EXPAND_BLOCK * EXPAND_SPT;
+  unsigned* item_off = item_cnt + MAX_GROUP_ITEMS;
   if (lane_id() == 0) *wcnt = 0;
   if (threadIdx.x == 0) *list_count = 0;
+  if (threadIdx.x < MAX_GROUP_ITEMS) item_cnt[threadIdx.x] = 0;
+  __syncthreads();
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
@@ -598,7 +629,8 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand2(Params p, uint64_t 
   const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
   for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
     for (int j = 0; j < spt; ++j) succ[j * EXPAND_BLOCK + threadIdx.x] = 0;
-    TwoPhaseCtx c{first, tile_base, count, spt, wbuf, wcnt, list, list_count, succ};
+    __syncthreads();                                   // succ[] zeroed before any body adds to it
+    TwoPhaseCtx c{first, tile_base, count, spt, wbuf, wcnt, list, list_count, succ, item_cnt, item_off};
     GroupRunner2<0, MULTI>::run(p, c, failed, xs);
     flush_stage<MULTI, false>(p, wbuf, wcnt, true, failed, xs);
     __syncthreads();                                   // every body of this tile has added to succ[]
@@ -928,7 +960,7 @@ static size_t expand_smem_bytes() {
   return (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
 }
 static size_t expand2_smem_bytes() {
-  return expand_smem_bytes() + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4;
+  return expand_smem_bytes() + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4 + 2 * MAX_GROUP_ITEMS * 4;
 }
 
 static int engine_alloc(Engine& E) {

@@ -286,6 +286,26 @@ def _render(nodes: list[_Node], depth: int) -> list[str]:
     return out
 
 
+def _split_unit(lines: list[str], max_blocks: int) -> list[list[str]]:
+    """Cuts a unit with many top-level blocks (e.g. an enumeration over an 80-element bitmap set) into
+    sub-units of at most ``max_blocks`` blocks; the unit's root-level temporaries are pure and are
+    replicated in every sub-unit."""
+    nodes = _prune(_parse_unit(lines))
+    temps = [n for n in nodes if not n.is_block and not n.text.startswith("else ")]
+    chunks: list[list[_Node]] = [[]]
+    count = 0
+    for n in nodes:
+        if n.is_block:
+            if count == max_blocks:
+                chunks.append([])
+                count = 0
+            chunks[-1].append(n)
+            count += 1
+        elif n.text.startswith("else "):
+            chunks[-1].append(n)
+    return [[l[2:] if l.startswith("  ") else l for l in _render(temps + c, 1)] for c in chunks if c]
+
+
 def _unit_items(lines: list[str], max_prefix_temps: int = 3):
     """Splits one unit into items.  An item = (guard temps, guard conditions, body lines): the
     guard is the chain of leading `if`s that are preceded by at most a few temporaries -- cheap to
@@ -502,13 +522,19 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     group_units: list[list[list[str]]] = []
     cur_lines: list[str] = []
     cur_units: list[list[str]] = []
+    cur_items = 0
+    all_units: list[list[str]] = []
     for lines, _ in lw.units:
-        if cur_lines and len(cur_lines) + len(lines) > group_lines:
+        all_units.extend(_split_unit(lines, 40) if len(_unit_items(lines)) > 40 else [lines])
+    for lines in all_units:
+        n_it = len(_unit_items(lines))
+        if cur_lines and (len(cur_lines) + len(lines) > group_lines or cur_items + n_it > 48):
             groups.append(cur_lines)
             group_units.append(cur_units)
-            cur_lines, cur_units = [], []
+            cur_lines, cur_units, cur_items = [], [], 0
         cur_lines = cur_lines + ["  {"] + ["  " + l for l in lines] + ["  }"]
         cur_units.append(lines)
+        cur_items += n_it
     if cur_lines or not groups:
         groups.append(cur_lines)
         group_units.append(cur_units)
@@ -616,6 +642,23 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
             parts.append("}")
             n_items += 1
     begins.append(n_items)
+    # one guard function per group: a single unpack, bit k = item (GROUP_ITEM_BEGIN[g] + k) is enabled
+    for gi, items in enumerate(group_items):
+        if len(items) > 64:
+            raise LowerError(f"group {gi} has {len(items)} items (> 64); lower group_lines")
+        parts.append(f"KMC_HD uint64_t group_guard_mask(GroupTag<{gi}>, const State& s) {{")
+        parts.extend(unpack)
+        parts.extend(expand_prologue)
+        parts.append("  uint64_t m = 0;")
+        for k, it in enumerate(items):
+            parts.append("  {")
+            parts.extend(it["root_temps"])
+            parts.extend(it["guard_temps"])
+            cond = " && ".join(f"({c})" for c in it["conds"]) if it["conds"] else "true"
+            parts.append(f"    if ({cond}) m |= 1ull << {k};")
+            parts.append("  }")
+        parts.append("  return m;")
+        parts.append("}")
     parts.append(f"static constexpr int NUM_ITEMS = {n_items};")
     parts.append("static constexpr int GROUP_ITEM_BEGIN[NUM_GROUPS + 1] = {" + ", ".join(str(b) for b in begins) + "};")
     parts.append("/* expand() through the two-phase form (used by tests to prove both forms agree) */")

@@ -245,3 +245,13 @@ def test_candidate_overflow_is_an_error_not_a_wrong_answer():
         assert e.value.code == -10
     with checker("frl_3x4x2", cand_bytes=1 << 20, fanout_bound=32) as ck:
         assert ck.run().distinct == 29791
+
+
+@pytest.mark.parametrize("name", ["kip320_small", "firsttry_small", "asyncisr_small", "frl_3x4x3", "kip320sym_n2", "idsequence"])
+def test_two_phase_expand_kernel_agrees(name, goldens):
+    """k_expand2 (guard-mask phase + CTA-wide compaction + body phase) against the goldens."""
+    g = goldens[name]
+    with checker(name, two_phase=True, cont=True) as ck:
+        r = ck.run()
+    assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
+        g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
