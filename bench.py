@@ -299,6 +299,8 @@ def run_sharded(args):
         opts["table_log2"] = args.table_log2
     if args.max_states:
         opts["max_states"] = args.max_states
+    if args.no_p2p:
+        opts["p2p"] = False
     eng = CudaShardEngine(args.model, rank, world, local, **opts)
     drv = ShardedChecker(eng)
     for _ in range(args.warmup):
@@ -347,6 +349,8 @@ def run_sharded(args):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic (the .cfg is the input; no RNG)",
             "config": config_for(args.model, {"distinct": N, "generated": G, "depth": res.depth, "state_words": W,
                                               "parity": parity, "parallelism": f"fingerprint-sharded x{world}",
+                                              "exchange": "fused: expand kernel stores rows into the owners' inboxes over NVLink (CUDA IPC)"
+                                              if eng.p2p else "NCCL all-to-all-v per chunk",
                                               "per_rank_distinct": res.per_rank_distinct,
                                               "exchanged_rows_per_step": res.exchanged_rows}),
             "roofline": {"kernel": "k_insert (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -374,6 +378,7 @@ def main():
     ap.add_argument("--table-log2", type=int, default=0)
     ap.add_argument("--max-states", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-to-all exchange instead of the fused peer-memory path")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

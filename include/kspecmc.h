@@ -154,6 +154,17 @@ int kmc_shard_insert(kmc_ctx* ctx, const uint64_t* rows_dev, uint64_t rows, uint
 int kmc_shard_level_done(kmc_ctx* ctx, uint64_t* level_first, uint64_t* level_count);
 int kmc_shard_sync(kmc_ctx* ctx);
 
+/* ---- fused expand + exchange over peer memory (NVLink): replaces counts/exchange/insert above ------
+ * Every rank owns an inbox (two buffers); kmc_shard_ipc_handle exports it (64-byte CUDA IPC handle),
+ * kmc_shard_open_peers maps all ranks' inboxes.  Per round: kmc_shard_expand_p2p (the expand kernel
+ * stores each successor row directly into its owner's inbox and publishes the row counts there) ->
+ * a cross-rank barrier enqueued by the caller on the engine's stream -> kmc_shard_insert_p2p.       */
+int kmc_shard_ipc_handle(kmc_ctx* ctx, void* out64);
+int kmc_shard_open_peers(kmc_ctx* ctx, const void* handles /* world x 64 bytes */, uint32_t world);
+int kmc_shard_seed_p2p(kmc_ctx* ctx);
+int kmc_shard_expand_p2p(kmc_ctx* ctx, uint64_t first, uint64_t count);
+int kmc_shard_insert_p2p(kmc_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,7 +129,16 @@ struct Params {
   uint32_t rank, world;
   uint32_t check_deadlock;
   uint32_t count_actions;
+  // fused exchange (world > 1, after kmc_shard_open_peers): every rank's inbox, mapped into this
+  // process through CUDA IPC.  An inbox is two buffers (double buffering); a buffer is an 8-word
+  // header (rows sent by each source rank) followed by world regions of region_rows rows.
+  uint64_t* peer_inbox[MAX_WORLD];
+  uint64_t inbox_stride;    // words per inbox buffer
+  uint32_t p2p;             // 1: expand stores rows straight into the owners' inboxes
+  uint32_t inbox_buf;       // which of the two buffers this round uses
 };
+
+static constexpr int INBOX_HEADER = 8;
 
 __device__ __forceinline__ unsigned lane_id() {
   unsigned r;
@@ -306,7 +315,11 @@ __device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t*
     failed = KMC_FAIL_CAND_FULL;
     return;
   }
-  uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + pos) * ROW;
+  // p2p: the row goes straight into region `rank` of the owner's inbox (a peer store over NVLink
+  // when dest != rank); otherwise into the local per-owner candidate region for a later exchange
+  uint64_t* row = p.p2p ? p.peer_inbox[dest] + (uint64_t)p.inbox_buf * p.inbox_stride + INBOX_HEADER +
+                              ((uint64_t)p.rank * p.region_rows + pos) * ROW
+                        : p.cand + ((uint64_t)dest * p.region_rows + pos) * ROW;
 #pragma unroll
   for (int i = 0; i < W; ++i) row[i] = s.w[i];
   row[W] = meta;
@@ -393,7 +406,9 @@ struct CandSink {
       if (gpos >= p.region_rows) {
         failed = KMC_FAIL_CAND_FULL;
       } else {
-        uint64_t* row = p.cand + ((uint64_t)dest * p.region_rows + gpos) * ROW;
+        uint64_t* row = p.p2p ? p.peer_inbox[dest] + (uint64_t)p.inbox_buf * p.inbox_stride + INBOX_HEADER +
+                                    ((uint64_t)p.rank * p.region_rows + gpos) * ROW
+                              : p.cand + ((uint64_t)dest * p.region_rows + gpos) * ROW;
 #pragma unroll
         for (int i = 0; i < W; ++i) row[i] = s.w[i];
         row[W] = meta;
@@ -763,6 +778,58 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
   }
 }
 
+// Fused exchange, step 2: tell every owner how many rows this rank stored in its inbox region.
+__global__ void k_publish_counts(Params p) {
+  unsigned d = threadIdx.x;
+  if (d < p.world) p.peer_inbox[d][(uint64_t)p.inbox_buf * p.inbox_stride + p.rank] = p.ctr->cand_count[d];
+}
+
+// Fused exchange, step 3 (after a cross-rank barrier): insert the rows of all source regions of
+// this rank's inbox buffer.  Row counts come from the header the sources wrote -- the host never
+// sees them.
+__global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
+  const uint64_t* inbox = p.peer_inbox[p.rank] + (uint64_t)p.inbox_buf * p.inbox_stride;
+  uint64_t starts[MAX_WORLD + 1];
+  starts[0] = 0;
+#pragma unroll
+  for (int r = 0; r < MAX_WORLD; ++r) {
+    uint64_t n = (r < (int)p.world) ? inbox[r] : 0;
+    if (n > p.region_rows) n = p.region_rows;
+    starts[r + 1] = starts[r] + n;
+  }
+  const uint64_t n = starts[MAX_WORLD];
+  const uint64_t n_round = (n + 31) & ~31ull;
+  unsigned probes = 0, oom = 0;
+  int failed = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool v0 = i < n;
+    State s0;
+    uint64_t m0 = 0;
+    if (v0) {
+      int src = 0;
+#pragma unroll
+      for (int r = 1; r < MAX_WORLD; ++r) src += (i >= starts[r]) ? 1 : 0;
+      const uint64_t* row = inbox + INBOX_HEADER + ((uint64_t)src * p.region_rows + (i - starts[src])) * ROW;
+#pragma unroll
+      for (int k = 0; k < W; ++k) s0.w[k] = __ldcs(row + k);
+      m0 = __ldcs(row + W);
+    }
+    Prefetched f0 = prefetch_row(p, s0, v0);
+    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    probes += __shfl_xor_sync(0xffffffffu, probes, o);
+    oom += __shfl_xor_sync(0xffffffffu, oom, o);
+    failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
+  }
+  if (lane_id() == 0) {
+    if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
+    if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
+    if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
+  }
+}
+
 // K3: invariants on the new states of a level.  They sit compacted in the store, so every lane
 // has work (inside k_insert only the ~1/3 of lanes holding a new state would be active).
 __global__ void __launch_bounds__(256) k_invariants(Params p, uint64_t first, const unsigned long long* end_ptr) {
@@ -832,6 +899,12 @@ struct Engine {
   uint64_t region_rows = 0;
   uint64_t* recv = nullptr;
   uint64_t recv_rows = 0;
+  uint64_t* inbox = nullptr;          // fused exchange: 2 x (header + world regions), shared through CUDA IPC
+  uint64_t inbox_stride = 0;
+  uint64_t* peer_inbox[MAX_WORLD] = {};
+  bool peers_open = false;
+  uint32_t inbox_buf = 0;
+  uint64_t exchanged_rows = 0;
   DevCounters* ctr = nullptr;
   uint64_t* viol_ring = nullptr;
   cudaStream_t stream = nullptr;
@@ -871,6 +944,10 @@ struct Engine {
     p.world = world;
     p.check_deadlock = check_deadlock ? 1 : 0;
     p.count_actions = count_actions ? 1 : 0;
+    for (int r = 0; r < MAX_WORLD; ++r) p.peer_inbox[r] = peer_inbox[r];
+    p.inbox_stride = inbox_stride;
+    p.p2p = 0;
+    p.inbox_buf = inbox_buf;
     return p;
   }
 };
@@ -1006,6 +1083,9 @@ static int engine_alloc(Engine& E) {
   if (E.world > 1) {
     E.recv_rows = E.region_rows * E.world;
     CK(cudaMalloc(&E.recv, E.recv_rows * ROW * 8));
+    E.inbox_stride = INBOX_HEADER + E.region_rows * E.world * ROW;
+    CK(cudaMalloc(&E.inbox, 2 * E.inbox_stride * 8));
+    CK(cudaMemset(E.inbox, 0, 2 * E.inbox_stride * 8));
   }
   // the expand kernels stage successor rows in > 48 KB of dynamic shared memory
   CK(cudaFuncSetAttribute(k_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
@@ -1337,6 +1417,10 @@ void kmcm_destroy(kmcm_ctx* c) {
   cudaFree(E.parent);
   cudaFree(E.cand);
   cudaFree(E.recv);
+  if (E.peers_open)
+    for (uint32_t r = 0; r < E.world; ++r)
+      if (r != E.rank && E.peer_inbox[r]) cudaIpcCloseMemHandle(E.peer_inbox[r]);
+  cudaFree(E.inbox);
   cudaFree(E.ctr);
   cudaFree(E.viol_ring);
   for (cudaEvent_t ev : E.event_pool) cudaEventDestroy(ev);
@@ -1467,6 +1551,7 @@ int kmcm_shard_begin(kmcm_ctx* c) {
   if (!c) return KMC_E_BADARG;
   int rc = engine_reset(E);
   if (rc) return rc;
+  E.inbox_buf = 0;
   E.shard_levels = 0;
   E.ran = false;
   CK(cudaEventRecord(E.ev_begin, E.stream));
@@ -1556,6 +1641,105 @@ int kmcm_shard_level_done(kmcm_ctx* c, uint64_t* level_first, uint64_t* level_co
   }
   if (h.viol_count && E.viol.kind == KMC_RESULT_OK) build_trace(E, h, E.shard_levels - 1);
   return fail_to_error(h.fail);
+}
+
+// ---- fused exchange over peer memory ---------------------------------------------------------
+int kmcm_shard_ipc_handle(kmcm_ctx* c, void* out64) {
+  if (!c || !out64 || !E.inbox) return KMC_E_BADARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaSetDevice(E.device));
+  CK(cudaIpcGetMemHandle(&h, E.inbox));
+  memcpy(out64, &h, 64);
+  return KMC_OK;
+}
+
+int kmcm_shard_open_peers(kmcm_ctx* c, const void* handles, uint32_t world) {
+  if (!c || !handles || world != E.world || !E.inbox) return KMC_E_BADARG;
+  CK(cudaSetDevice(E.device));
+  for (uint32_t r = 0; r < world; ++r) {
+    if (r == E.rank) {
+      E.peer_inbox[r] = E.inbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    E.peer_inbox[r] = (uint64_t*)ptr;
+  }
+  E.peers_open = true;
+  return KMC_OK;
+}
+
+// expand a frontier chunk, storing every successor row directly into its owner's inbox, then
+// publish the per-owner row counts into the owners' inbox headers (both on the engine stream)
+int kmcm_shard_expand_p2p(kmcm_ctx* c, uint64_t first, uint64_t count) {
+  if (!c || !E.peers_open) return KMC_E_STATE;
+  if (count > E.chunk_states) return KMC_E_BADARG;
+  int rc = reset_cand(E);
+  if (rc) return rc;
+  Params p = E.params();
+  p.p2p = 1;
+  if (count) {
+    int spt = EXPAND_SPT;
+    while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
+    uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
+    int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
+    TimedLaunch t(E, 0);
+    k_expand<true, false><<<grid, EXPAND_BLOCK, expand_smem_bytes(), E.stream>>>(p, first, count, spt);
+  }
+  {
+    TimedLaunch t(E, 2);
+    k_publish_counts<<<1, 32, 0, E.stream>>>(p);
+  }
+  CK(cudaGetLastError());
+  return KMC_OK;
+}
+
+// seed: the initial states go through the same inbox path (rank 0 contributes them)
+int kmcm_shard_seed_p2p(kmcm_ctx* c) {
+  if (!c || !E.peers_open) return KMC_E_STATE;
+  CK(cudaSetDevice(E.device));
+  unsigned long long counts[MAX_WORLD] = {0};
+  if (E.rank == 0) {
+    for (int i = 0; i < M::NUM_INIT; ++i) {
+      State s;
+      memcpy(s.w, M::INIT_STATES[i], sizeof(s.w));
+      uint32_t d = owner_of(state_fp(s), E.world);
+      uint64_t row[ROW];
+      for (int k = 0; k < W; ++k) row[k] = s.w[k];
+      row[W] = NO_PARENT;
+      uint64_t* dst = E.peer_inbox[d] + (uint64_t)E.inbox_buf * E.inbox_stride + INBOX_HEADER +
+                      ((uint64_t)E.rank * E.region_rows + counts[d]) * ROW;
+      CK(cudaMemcpyAsync(dst, row, sizeof(row), cudaMemcpyHostToDevice, E.stream));
+      CK(cudaStreamSynchronize(E.stream));
+      counts[d]++;
+    }
+    unsigned long long gen = M::NUM_INIT;
+    CK(cudaMemcpyAsync(&E.ctr->generated, &gen, sizeof(gen), cudaMemcpyHostToDevice, E.stream));
+  }
+  CK(cudaMemcpyAsync(E.ctr, counts, sizeof(counts), cudaMemcpyHostToDevice, E.stream));
+  Params p = E.params();
+  p.p2p = 1;
+  k_publish_counts<<<1, 32, 0, E.stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(E.stream));
+  return KMC_OK;
+}
+
+// insert everything the peers stored into the current inbox buffer, then switch buffers.
+// The caller must have put a cross-rank barrier on the stream between expand_p2p and this call.
+int kmcm_shard_insert_p2p(kmcm_ctx* c) {
+  if (!c || !E.peers_open) return KMC_E_STATE;
+  Params p = E.params();
+  {
+    TimedLaunch t(E, 1);
+    k_insert_inbox<<<E.sms * 8, 256, 0, E.stream>>>(p);
+  }
+  CK(cudaGetLastError());
+  E.inbox_buf ^= 1;
+  return KMC_OK;
 }
 
 int kmcm_shard_sync(kmcm_ctx* c) {

@@ -43,6 +43,11 @@ struct kmc_ctx {
   int (*shard_insert)(kmcm_ctx*, const uint64_t*, uint64_t, uint64_t*) = nullptr;
   int (*shard_level_done)(kmcm_ctx*, uint64_t*, uint64_t*) = nullptr;
   int (*shard_sync)(kmcm_ctx*) = nullptr;
+  int (*shard_ipc_handle)(kmcm_ctx*, void*) = nullptr;
+  int (*shard_open_peers)(kmcm_ctx*, const void*, uint32_t) = nullptr;
+  int (*shard_seed_p2p)(kmcm_ctx*) = nullptr;
+  int (*shard_expand_p2p)(kmcm_ctx*, uint64_t, uint64_t) = nullptr;
+  int (*shard_insert_p2p)(kmcm_ctx*) = nullptr;
 };
 
 template <class F>
@@ -78,7 +83,9 @@ int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out) {
             bind(c, c->shard_seed_init, "kmcm_shard_seed_init") && bind(c, c->shard_expand, "kmcm_shard_expand") &&
             bind(c, c->shard_counts, "kmcm_shard_counts") && bind(c, c->shard_reset_cand, "kmcm_shard_reset_cand") &&
             bind(c, c->shard_insert, "kmcm_shard_insert") && bind(c, c->shard_level_done, "kmcm_shard_level_done") &&
-            bind(c, c->shard_sync, "kmcm_shard_sync");
+            bind(c, c->shard_sync, "kmcm_shard_sync") && bind(c, c->shard_ipc_handle, "kmcm_shard_ipc_handle") &&
+            bind(c, c->shard_open_peers, "kmcm_shard_open_peers") && bind(c, c->shard_seed_p2p, "kmcm_shard_seed_p2p") &&
+            bind(c, c->shard_expand_p2p, "kmcm_shard_expand_p2p") && bind(c, c->shard_insert_p2p, "kmcm_shard_insert_p2p");
   if (!ok) return KMC_E_MODEL;
   return c->create(options_json, &c->inner);
 }
@@ -120,5 +127,10 @@ int kmc_shard_reset_cand(kmc_ctx* c) { FWD(shard_reset_cand); }
 int kmc_shard_insert(kmc_ctx* c, const uint64_t* rows, uint64_t n, uint64_t* tail) { FWD(shard_insert, rows, n, tail); }
 int kmc_shard_level_done(kmc_ctx* c, uint64_t* first, uint64_t* count) { FWD(shard_level_done, first, count); }
 int kmc_shard_sync(kmc_ctx* c) { FWD(shard_sync); }
+int kmc_shard_ipc_handle(kmc_ctx* c, void* out64) { FWD(shard_ipc_handle, out64); }
+int kmc_shard_open_peers(kmc_ctx* c, const void* h, uint32_t world) { FWD(shard_open_peers, h, world); }
+int kmc_shard_seed_p2p(kmc_ctx* c) { FWD(shard_seed_p2p); }
+int kmc_shard_expand_p2p(kmc_ctx* c, uint64_t first, uint64_t count) { FWD(shard_expand_p2p, first, count); }
+int kmc_shard_insert_p2p(kmc_ctx* c) { FWD(shard_insert_p2p); }
 
 }  // extern "C"

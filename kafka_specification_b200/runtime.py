@@ -103,10 +103,17 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.kmc_shard_insert.argtypes = [vp, vp, ctypes.c_uint64, u64p]
     lib.kmc_shard_level_done.argtypes = [vp, u64p, u64p]
     lib.kmc_shard_sync.argtypes = [vp]
+    lib.kmc_shard_ipc_handle.argtypes = [vp, vp]
+    lib.kmc_shard_open_peers.argtypes = [vp, vp, ctypes.c_uint32]
+    lib.kmc_shard_seed_p2p.argtypes = [vp]
+    lib.kmc_shard_expand_p2p.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64]
+    lib.kmc_shard_insert_p2p.argtypes = [vp]
     for fn in ("kmc_create", "kmc_model_info", "kmc_run", "kmc_stats", "kmc_level_widths", "kmc_action_counts",
                "kmc_violation", "kmc_trace_state", "kmc_copy_states", "kmc_fpset_put", "kmc_fpset_contains",
                "kmc_fpset_size", "kmc_shard_begin", "kmc_shard_buffers", "kmc_shard_seed_init", "kmc_shard_expand",
-               "kmc_shard_counts", "kmc_shard_reset_cand", "kmc_shard_insert", "kmc_shard_level_done", "kmc_shard_sync"):
+               "kmc_shard_counts", "kmc_shard_reset_cand", "kmc_shard_insert", "kmc_shard_level_done", "kmc_shard_sync",
+               "kmc_shard_ipc_handle", "kmc_shard_open_peers", "kmc_shard_seed_p2p", "kmc_shard_expand_p2p",
+               "kmc_shard_insert_p2p"):
         getattr(lib, fn).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -263,7 +270,7 @@ class Checker:
             self.meta = json.load(f)
         self.decoder = StateDecoder(self.meta)
         self.ctx = ctypes.c_void_p()
-        opts = {("continue" if k == "cont" else k): v for k, v in options.items()}
+        opts = {("continue" if k == "cont" else k): v for k, v in options.items() if k != "p2p"}
         rc = self.lib.kmc_create(self.model_lib.encode(), json.dumps(opts).encode(), ctypes.byref(self.ctx))
         if rc != 0:
             msg = self.lib.kmc_strerror(self.ctx, rc).decode() if self.ctx else "kmc_create failed"

@@ -89,6 +89,38 @@ class CudaShardEngine(ShardEngine):
         self._cand_ptr = b.cand
         self.counts_dev = torch.as_tensor(_DevArray(b.cand_counts, 8), device=self.device)[:world]
         self._matrix = torch.empty(world * world, dtype=torch.int64, device=self.device)
+        self.p2p = False
+        if world > 1 and options.get("p2p", True) and dist.is_initialized():
+            self._open_peers()
+
+    def _open_peers(self):
+        """Map every rank's inbox into this process (CUDA IPC) so that the expand kernel can store
+        successor rows straight into their owner's memory over NVLink."""
+        h = (ctypes.c_ubyte * 64)()
+        self.ck._check(self.lib.kmc_shard_ipc_handle(self.ck.ctx, h))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(h))
+        blob = b"".join(handles)
+        rc = self.lib.kmc_shard_open_peers(self.ck.ctx, blob, self.world)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self.p2p = bool(ok.item())
+        if not self.p2p and self.rank == 0:
+            print(f"[kspec-mc] CUDA IPC peer mapping unavailable (rc={rc}); using the NCCL all-to-all exchange")
+        self._flag = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def seed_p2p(self):
+        self.ck._check(self.lib.kmc_shard_seed_p2p(self.ck.ctx))
+
+    def expand_p2p(self, first, count):
+        self.ck._check(self.lib.kmc_shard_expand_p2p(self.ck.ctx, first, count))
+
+    def insert_p2p(self):
+        self.ck._check(self.lib.kmc_shard_insert_p2p(self.ck.ctx))
+
+    def barrier_on_stream(self, group=None):
+        """Cross-rank barrier ordered on the engine's stream; the host does not wait."""
+        dist.all_reduce(self._flag, group=group)
 
     def begin(self):
         self.ck._check(self.lib.kmc_shard_begin(self.ck.ctx))
@@ -222,6 +254,15 @@ class ShardedChecker:
     def _round(self, first: int, count: int, init: bool = False):
         """One expand -> exchange -> insert round on a frontier chunk (count may be 0 on idle ranks)."""
         e = self.e
+        if getattr(e, "p2p", False):
+            # fused path: rows were stored into the owners' inboxes by the expand kernel itself
+            if init:
+                e.seed_p2p()
+            else:
+                e.expand_p2p(first, count)
+            e.barrier_on_stream(self.group)
+            e.insert_p2p()
+            return
         if not init:
             e.reset_cand()
             if count:
@@ -264,7 +305,8 @@ class ShardedChecker:
             dist.barrier(group=self.group)
         t0 = time.perf_counter()
         e.begin()
-        e.seed_init()
+        if not getattr(e, "p2p", False):
+            e.seed_init()
         self._round(0, 0, init=True)
         first, count = e.level_done()
         levels: list[int] = []
