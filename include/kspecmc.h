@@ -122,6 +122,12 @@ int kmc_violation(const kmc_ctx* ctx, kmc_violation_t* out);
 int kmc_trace_state(const kmc_ctx* ctx, uint32_t i, uint64_t* buf, size_t cap_words, uint32_t* action_id);
 /* copy packed states [first, first+count) of the state store to host memory               */
 int kmc_copy_states(const kmc_ctx* ctx, uint64_t first, uint64_t count, uint64_t* buf);
+/* parent words of the same range: bits 0..39 store index, 40..47 owner rank of the parent,
+ * 56..63 action id; low 48 bits all ones = initial state (TLC's trace file)                 */
+int kmc_copy_parents(const kmc_ctx* ctx, uint64_t first, uint64_t count, uint64_t* buf);
+/* this rank's offending state (packed words) and its parent word -- the starting point of a trace
+ * walk that crosses ranks (a multi-rank driver follows parent words through kmc_copy_*)      */
+int kmc_violation_record(const kmc_ctx* ctx, uint64_t* words, size_t cap_words, uint64_t* parent_word);
 const char* kmc_strerror(const kmc_ctx* ctx, int code);
 
 /* ---- fingerprint set alone (FPSet.put / contains / size) ------------------------------ */

@@ -924,6 +924,8 @@ struct Engine {
   kmc_violation_t viol{};
   std::vector<std::vector<uint64_t>> trace;
   std::vector<uint32_t> trace_actions;
+  std::vector<uint64_t> viol_words;     // the offending state itself and its parent/action word
+  uint64_t viol_meta = 0;
   bool ran = false;
   uint64_t level_first = 0, level_count = 0;   // shard API
   uint64_t shard_levels = 0;
@@ -1236,6 +1238,8 @@ static int build_trace(Engine& E, const DevCounters& h, uint64_t level) {
   std::vector<std::vector<uint64_t>> rev;
   std::vector<uint32_t> rev_act;
   uint64_t meta = best[W];
+  E.viol_words.assign(best, best + W);
+  E.viol_meta = meta;
   rev.push_back(std::vector<uint64_t>(best, best + W));
   rev_act.push_back((uint32_t)(meta >> 56));
   uint64_t guard = 0;
@@ -1486,6 +1490,24 @@ int kmcm_trace_state(const kmcm_ctx* c, uint32_t i, uint64_t* buf, size_t cap_wo
   if (i >= E.trace.size() || cap_words < (size_t)W) return KMC_E_BADARG;
   memcpy(buf, E.trace[i].data(), W * 8);
   if (action_id) *action_id = E.trace_actions[i];
+  return KMC_OK;
+}
+
+// the offending state of this rank (before any cross-rank trace walk): packed words + parent/action word
+int kmcm_violation_record(const kmcm_ctx* c, uint64_t* words, size_t cap_words, uint64_t* parent_meta) {
+  if (!c || !words || !parent_meta || cap_words < (size_t)W) return KMC_E_BADARG;
+  if (E.viol.kind == KMC_RESULT_OK || E.viol_words.size() != (size_t)W) return KMC_E_STATE;
+  memcpy(words, E.viol_words.data(), W * 8);
+  *parent_meta = E.viol_meta;
+  return KMC_OK;
+}
+
+int kmcm_copy_parents(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64_t* buf) {
+  kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
+  if (!c || !buf) return KMC_E_BADARG;
+  if (first + count > E.max_states) return KMC_E_BADARG;
+  CK(cudaSetDevice(E.device));
+  CK(cudaMemcpy(buf, E.parent + first, count * 8, cudaMemcpyDeviceToHost));
   return KMC_OK;
 }
 

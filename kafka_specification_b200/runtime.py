@@ -89,6 +89,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.kmc_violation.argtypes = [vp, ctypes.POINTER(Violation)]
     lib.kmc_trace_state.argtypes = [vp, ctypes.c_uint32, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
     lib.kmc_copy_states.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.kmc_copy_parents.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.kmc_violation_record.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
     lib.kmc_strerror.argtypes = [vp, ctypes.c_int]
     lib.kmc_strerror.restype = ctypes.c_char_p
     lib.kmc_fpset_put.argtypes = [vp, vp, ctypes.c_size_t, vp]
@@ -109,7 +111,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.kmc_shard_expand_p2p.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64]
     lib.kmc_shard_insert_p2p.argtypes = [vp]
     for fn in ("kmc_create", "kmc_model_info", "kmc_run", "kmc_stats", "kmc_level_widths", "kmc_action_counts",
-               "kmc_violation", "kmc_trace_state", "kmc_copy_states", "kmc_fpset_put", "kmc_fpset_contains",
+               "kmc_violation", "kmc_trace_state", "kmc_copy_states", "kmc_copy_parents", "kmc_violation_record", "kmc_fpset_put", "kmc_fpset_contains",
                "kmc_fpset_size", "kmc_shard_begin", "kmc_shard_buffers", "kmc_shard_seed_init", "kmc_shard_expand",
                "kmc_shard_counts", "kmc_shard_reset_cand", "kmc_shard_insert", "kmc_shard_level_done", "kmc_shard_sync",
                "kmc_shard_ipc_handle", "kmc_shard_open_peers", "kmc_shard_seed_p2p", "kmc_shard_expand_p2p",
@@ -362,6 +364,21 @@ class Checker:
         return RunResult(distinct=st["distinct"], generated=st["generated"], depth=st["depth"], queue=st["queue"],
                          deadlocks=st["deadlocks"], complete=bool(st["complete"]), levels=self.level_widths(),
                          stats=st, violation=viol, trace=self.trace() if viol else [])
+
+    def violation_record(self):
+        """(packed words, parent word) of this rank's offending state, or None."""
+        buf = (ctypes.c_uint64 * self.words)()
+        meta = ctypes.c_uint64()
+        rc = self.lib.kmc_violation_record(self.ctx, buf, self.words, ctypes.byref(meta))
+        if rc != 0:
+            return None
+        return [int(buf[k]) for k in range(self.words)], int(meta.value)
+
+    def state_and_parent(self, idx: int):
+        st = self.copy_states(idx, 1)[0]
+        par = np.empty(1, dtype=np.uint64)
+        self._check(self.lib.kmc_copy_parents(self.ctx, idx, 1, par.ctypes.data))
+        return [int(x) for x in st], int(par[0])
 
     def copy_states(self, first: int, count: int) -> np.ndarray:
         buf = np.empty((count, self.words), dtype=np.uint64)

@@ -178,6 +178,19 @@ class CudaShardEngine(ShardEngine):
     def violation(self):
         return self.ck.violation()
 
+    def violation_record(self):
+        return self.ck.violation_record()
+
+    def state_and_parent(self, idx):
+        return self.ck.state_and_parent(idx)
+
+    def describe_state(self, words):
+        return self.ck.decoder.text(words)
+
+    def action_name(self, aid):
+        acts = self.ck.meta["actions"]
+        return acts[aid]["name"] if aid < len(acts) else None
+
     def trace(self):
         return self.ck.trace()
 
@@ -198,6 +211,7 @@ class ShardedResult:
     seconds: float
     exchanged_rows: int
     stats: dict = field(default_factory=dict)
+    trace: list = field(default_factory=list)      # error trace across ranks: [{"words", "action", "rank", "text"}]
 
 
 class ShardedChecker:
@@ -333,10 +347,62 @@ class ShardedChecker:
         seconds = time.perf_counter() - t0
         if self.world > 1:
             seconds = self._all_reduce_max_float(seconds)
+        any_viol = max(self._all_reduce([1 if e.violation() else 0], op=dist.ReduceOp.MAX)) if self.world > 1 \
+            else (1 if e.violation() else 0)
+        viol, trace = (self._global_violation() if (any_viol and hasattr(e, "violation_record")) else (e.violation(), []))
         return ShardedResult(distinct=sum(r[0] for r in rows), generated=sum(r[1] for r in rows), depth=len(levels),
                              deadlocks=sum(r[2] for r in rows), levels=levels, complete=not stopped,
-                             violation=e.violation(), per_rank_distinct=[r[0] for r in rows], seconds=seconds,
-                             exchanged_rows=self.exchanged, stats=st)
+                             violation=viol, per_rank_distinct=[r[0] for r in rows], seconds=seconds,
+                             exchanged_rows=self.exchanged, stats=st, trace=trace)
+
+    # -- error trace across ranks ----------------------------------------------
+    NO_PARENT = 0x0000FFFFFFFFFFFF
+
+    def _gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def _global_violation(self):
+        """All ranks agree on one offending state: deadlocks (they belong to the level being expanded)
+        before invariant violations, then the smallest fingerprint -- the same rule as on one GPU --
+        and walk its parent links back to an initial state, hopping ranks as the links do."""
+        e = self.e
+        v = e.violation()
+        rec = e.violation_record() if v else None
+        mine = None
+        if v and rec:
+            mine = {"rank": self.rank, "kind": v["kind"], "invariant": v.get("invariant"), "level": v["level"],
+                    "fingerprint": v["fingerprint"], "words": rec[0], "meta": rec[1]}
+        cands = [c for c in self._gather_objects(mine) if c]
+        if not cands:
+            return None, []
+        best = min(cands, key=lambda c: (0 if c["kind"] == "deadlock" else 1, c["fingerprint"], c["rank"]))
+        chain = [(best["words"], best["meta"], best["rank"])]
+        meta = best["meta"]
+        for _ in range(100000):
+            if (meta & self.NO_PARENT) == self.NO_PARENT:
+                break
+            prank, idx = (meta >> 40) & 0xFF, meta & 0xFFFFFFFFFF
+            fetched = e.state_and_parent(idx) if prank == self.rank else None
+            got = [g for g in self._gather_objects(fetched) if g]
+            words, pmeta = got[0]
+            chain.append((words, pmeta, prank))
+            meta = pmeta
+        chain.reverse()
+        trace = []
+        for i, (words, m, r) in enumerate(chain):
+            aid = (m >> 56) & 0xFF
+            entry = {"words": words, "rank": r, "action": None if i == 0 else aid}
+            if hasattr(e, "describe_state"):
+                entry["text"] = e.describe_state(words)
+                entry["action_name"] = None if i == 0 else e.action_name(aid)
+            trace.append(entry)
+        viol = {k: best[k] for k in ("kind", "invariant", "level", "fingerprint", "rank")}
+        viol["trace_len"] = len(trace)
+        return viol, trace
 
     def _all_reduce_max_float(self, x: float) -> float:
         t = torch.tensor([x], dtype=torch.float64, device=self.e.device)

@@ -20,11 +20,16 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     eng = HostShardEngine(name, rank, world, chunk_states=chunk)
     res = ShardedChecker(eng, cont=cont).run()
+    trace_ok = None
+    if res.trace:
+        steps = [t["words"] for t in res.trace]
+        trace_ok = bool(eng.is_init(steps[0])) and all(eng.is_successor(a, b) >= 0 for a, b in zip(steps, steps[1:]))
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump({"distinct": res.distinct, "generated": res.generated, "depth": res.depth,
                        "deadlocks": res.deadlocks, "levels": res.levels, "complete": res.complete,
-                       "violation": res.violation, "per_rank": res.per_rank_distinct,
+                       "violation": res.violation, "per_rank": res.per_rank_distinct, "trace_len": len(res.trace),
+                       "trace_ok": trace_ok, "trace_ranks": sorted({t["rank"] for t in res.trace}),
                        "exchanged_rows": res.exchanged_rows}, f)
     dist.barrier()
     dist.destroy_process_group()

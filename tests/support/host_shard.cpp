@@ -32,6 +32,9 @@ struct Rank {
   uint32_t rank, world;
   std::unordered_set<State, StateHash, StateEq> seen;
   std::vector<State> store;
+  std::vector<uint64_t> parent;
+  State viol_state;
+  uint64_t viol_meta = 0, viol_fp = ~0ull, viol_level = 0, level = 0;
   std::vector<std::vector<uint64_t>> cand;
   std::vector<uint64_t> recv;
   uint64_t generated = 0, deadlocks = 0, level_first = 0, level_count = 0;
@@ -59,7 +62,8 @@ void* hs_create(uint32_t rank, uint32_t world) {
 void hs_destroy(void* h) { delete (Rank*)h; }
 void hs_begin(void* h) {
   Rank* r = (Rank*)h;
-  r->seen.clear(); r->store.clear();
+  r->seen.clear(); r->store.clear(); r->parent.clear();
+  r->viol_fp = ~0ull; r->viol_level = 0; r->level = 0;
   for (auto& c : r->cand) c.clear();
   r->generated = r->deadlocks = r->level_first = r->level_count = 0;
   r->viol_inv = -1; r->fail = 0;
@@ -101,14 +105,23 @@ void hs_insert(void* h, const uint64_t* rows, uint64_t n) {
     State s; memcpy(s.w, rows + i * ROW, sizeof(s.w));
     bool inmodel = kmc_model::in_model(s);
     bool is_new = inmodel && r->seen.insert(s).second;
-    if (is_new) r->store.push_back(s);
-    if ((is_new || !inmodel) && r->viol_inv < 0) r->viol_inv = kmc_model::first_violated_invariant(s);
+    uint64_t meta = rows[i * ROW + W];
+    if (is_new) { r->store.push_back(s); r->parent.push_back(meta); }
+    if (is_new || !inmodel) {
+      int inv = kmc_model::first_violated_invariant(s);
+      uint64_t fp = fingerprint(s);
+      if (inv >= 0 && (r->viol_inv < 0 || r->viol_level == r->level + 1) && fp < r->viol_fp) {
+        if (r->viol_inv < 0) r->viol_level = r->level + 1;
+        r->viol_inv = inv; r->viol_fp = fp; r->viol_state = s; r->viol_meta = meta;
+      }
+    }
   }
 }
 void hs_level_done(void* h, uint64_t* first, uint64_t* count) {
   Rank* r = (Rank*)h;
   r->level_first += r->level_count;
   r->level_count = r->store.size() - r->level_first;
+  r->level++;
   *first = r->level_first; *count = r->level_count;
 }
 void hs_stats(void* h, uint64_t* out) {
@@ -117,4 +130,28 @@ void hs_stats(void* h, uint64_t* out) {
   out[4] = (uint64_t)r->viol_inv;
 }
 int hs_row_words() { return ROW; }
+// violation record: out[0..W) words, out[W] parent word, out[W+1] fingerprint, out[W+2] level; returns invariant or -1
+int hs_violation_record(void* h, uint64_t* out) {
+  Rank* r = (Rank*)h;
+  if (r->viol_inv < 0) return -1;
+  memcpy(out, r->viol_state.w, sizeof(r->viol_state.w));
+  out[W] = r->viol_meta; out[W + 1] = r->viol_fp; out[W + 2] = r->viol_level;
+  return (int)r->viol_inv;
+}
+void hs_state_and_parent(void* h, uint64_t idx, uint64_t* out) {
+  Rank* r = (Rank*)h;
+  memcpy(out, r->store[idx].w, sizeof(uint64_t) * W);
+  out[W] = r->parent[idx];
+}
+int hs_is_successor(const uint64_t* a, const uint64_t* b) {
+  struct Find { const State* t; int found = -1; void emit(const State& n, int act) { if (found < 0 && memcmp(n.w, t->w, sizeof(n.w)) == 0) found = act; } void fail(int) {} };
+  State s, t; memcpy(s.w, a, sizeof(s.w)); memcpy(t.w, b, sizeof(t.w));
+  Find f; f.t = &t;
+  kmc_model::expand(s, f);
+  return f.found;
+}
+int hs_is_init(const uint64_t* a) {
+  for (int i = 0; i < kmc_model::NUM_INIT; ++i) if (memcmp(kmc_model::INIT_STATES[i], a, sizeof(uint64_t) * W) == 0) return 1;
+  return 0;
+}
 }

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 
 def build(name: str) -> ctypes.CDLL:
     hdr = os.path.join(ROOT, "build", "models", name, "model.h")
-    tag = hashlib.sha256(open(hdr, "rb").read()).hexdigest()[:12]
+    tag = hashlib.sha256(open(hdr, "rb").read() + open(os.path.join(HERE, "host_shard.cpp"), "rb").read()).hexdigest()[:12]
     out = os.path.join(ROOT, "build", "hosttest")
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, f"shard_{name}_{tag}.so")
@@ -117,6 +117,38 @@ class HostShardEngine:
         st = self._raw()
         return {"distinct": int(st[0]), "generated": int(st[1]), "deadlocks": int(st[2]), "fail": int(st[3])}
 
+    def _record(self):
+        out = np.zeros(self.row_words + 4, dtype=np.uint64)
+        self.lib.hs_violation_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        inv = self.lib.hs_violation_record(self.h, out.ctypes.data)
+        return inv, out
+
     def violation(self):
-        v = int(self._raw()[4].astype(np.int64))
-        return None if v < 0 else {"kind": "invariant", "invariant_index": v}
+        inv, out = self._record()
+        if inv < 0:
+            return None
+        W = self.row_words - 1
+        return {"kind": "invariant", "invariant": inv, "level": int(out[W + 2]), "fingerprint": int(out[W + 1])}
+
+    def violation_record(self):
+        inv, out = self._record()
+        if inv < 0:
+            return None
+        W = self.row_words - 1
+        return [int(x) for x in out[:W]], int(out[W])
+
+    def state_and_parent(self, idx):
+        out = np.zeros(self.row_words, dtype=np.uint64)
+        self.lib.hs_state_and_parent.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        self.lib.hs_state_and_parent(self.h, idx, out.ctypes.data)
+        return [int(x) for x in out[:-1]], int(out[-1])
+
+    def is_successor(self, a, b) -> int:
+        self.lib.hs_is_successor.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        x, y = np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64)
+        return self.lib.hs_is_successor(x.ctypes.data, y.ctypes.data)
+
+    def is_init(self, a) -> int:
+        self.lib.hs_is_init.argtypes = [ctypes.c_void_p]
+        x = np.array(a, dtype=np.uint64)
+        return self.lib.hs_is_init(x.ctypes.data)

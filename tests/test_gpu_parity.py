@@ -255,3 +255,38 @@ def test_two_phase_expand_kernel_agrees(name, goldens):
         r = ck.run()
     assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
         g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+
+
+def _torchrun(script_args, port):
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args,
+                         capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    return json.loads(line[-1])
+
+
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_violation_and_cross_rank_trace(mode, goldens):
+    """2 ranks: stop at the first violating level, agree on one offending state, and walk its parent
+    links across the two GPUs' stores back to the initial state (both exchange paths)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = goldens["trunchw_small"]
+    first = min(l for l in g["first_violation_level"].values() if l)
+    r = _torchrun([os.path.join(ROOT, "tools", "sharded_check.py"), "trunchw_small", mode], 29541 if mode == "p2p" else 29542)
+    assert r["p2p"] == (mode == "p2p")
+    assert not r["complete"] and r["violation"]["kind"] == "invariant" and r["violation"]["level"] == first
+    assert r["depth"] == first - 1 and r["levels"] == g["levels"][: first - 1]
+    assert len(r["trace"]) == first and r["trace"][0]["action"] is None
+    assert len({t["rank"] for t in r["trace"]}) == 2
+    with checker("trunchw_small") as ck:
+        trace = [{"words": t["words"]} for t in r["trace"]]
+        _assert_trace_is_behaviour("trunchw_small", trace, ck)
+    # and the full search past the violation still matches the golden
+    r = _torchrun([os.path.join(ROOT, "tools", "sharded_check.py"), "trunchw_small", mode, "cont"], 29543 if mode == "p2p" else 29544)
+    assert (r["distinct"], r["generated"], r["depth"], r["levels"]) == (g["distinct"], g["generated"], g["depth"], g["levels"])

@@ -54,5 +54,8 @@ def test_sharded_bfs_stops_on_violation(tmp_path, goldens):
     first = min(l for l in g["first_violation_level"].values() if l)
     assert r["violation"] is not None and not r["complete"]
     assert r["depth"] == first - 1                          # levels fully expanded before the violating one
+    # the error trace is walked across ranks through the parent words: shortest, and a real behaviour
+    assert r["violation"]["level"] == first and r["trace_len"] == first and r["trace_ok"] is True
+    assert len(r["trace_ranks"]) == 2                       # it does hop between the two ranks' stores
     r = _run("trunchw_n2", 2, 200, tmp_path, extra=("cont",))
     assert (r["distinct"], r["generated"], r["depth"]) == (g["distinct"], g["generated"], g["depth"])
