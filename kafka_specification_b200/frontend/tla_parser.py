@@ -14,7 +14,7 @@ AST = plain tuples, first element the node kind:
   ('and', [items]) ('or', [items])      junction lists and infix chains, flattened
   ('quant', 'E'|'A', [([names], set)], body)
   ('choose', name, set, body)
-  ('if', c, t, e) ('let', [Def], body)
+  ('if', c, t, e) ('let', [Def], body) ('case', [(guard, e)], other|None)
   ('setenum', [items]) ('setmap', expr, [([names], set)]) ('setfilter', name, set, pred)
   ('subset', e) ('union_all', e) ('domain', e)
   ('fnlit', [([names], set)], body) ('fnapp', f, [args]) ('fnset', S, T)
@@ -311,6 +311,24 @@ class Parser:
                 return ("if", c, a, b)
             if t.text == "LET":
                 return self.parse_let()
+            if t.text == "CASE":
+                # CASE p1 -> e1 [] p2 -> e2 [] OTHER -> e   ==> ('case', [(p, e)...], other | None)
+                self.advance()
+                arms, other = [], None
+                while True:
+                    if self.is_kw("OTHER"):
+                        self.advance()
+                        self.expect_op("->")
+                        other = self.parse_expr()
+                    else:
+                        g = self.parse_expr()
+                        self.expect_op("->")
+                        arms.append((g, self.parse_expr()))
+                    if self.is_op("[]") and not self.blocked():
+                        self.advance()
+                        continue
+                    break
+                return ("case", arms, other)
             if t.text == "CHOOSE":
                 self.advance()
                 name = self.expect_id()

@@ -758,6 +758,18 @@ class Lowerer:
         if k in ("app", "inst"):
             op = self.find_operator(e, ctx, fm, env)
             if op is None:
+                if k == "app" and e[1] == "Cardinality" and len(e[2]) == 1:
+                    # FiniteSets: number of distinct present elements = sum of the (de-duplicated) guards
+                    sv = self.ev(e[2][0], ctx, fm, env, S)
+                    if isinstance(sv, frozenset):
+                        return len(sv)
+                    items = self.distinct_items(sv)
+                    fixed = sum(1 for g, _ in items if g is True)
+                    dyn = [g for g, _ in items if g is not True]
+                    if not dyn:
+                        return fixed
+                    terms = ([str(fixed)] if fixed else []) + [f"(int){g.s}" for g in dyn]
+                    return SInt(self.tmp_int("(" + " + ".join(terms) + ")"), fixed, fixed + len(dyn))
                 if k == "app" and e[1] == "Permutations" and len(e[2]) == 1:
                     # TLC module: all permutations of a constant finite set (used by SYMMETRY)
                     base = self.ev(e[2][0], ctx, fm, env, S)
@@ -794,6 +806,21 @@ class Lowerer:
             return self.mux(c, self.ev(e[2], ctx, fm, env, S), self.ev(e[3], ctx, fm, env, S))
         if k == "let":
             return self.ev(e[2], ctx, fm, self.let_env(e[1], ctx, fm, env), S)
+        if k == "case":
+            # CASE p1 -> e1 [] ... [] OTHER -> e: a select chain (the first true guard wins, like TLC)
+            if e[2] is not None:
+                res = self.ev(e[2], ctx, fm, env, S)
+                arms = e[1]
+            else:
+                res = self.ev(e[1][-1][1], ctx, fm, env, S)      # no OTHER: the last arm is the fall-through
+                arms = e[1][:-1]
+            for g, x in reversed(arms):
+                c = self.ev_bool(g, ctx, fm, env, S)
+                if c is True:
+                    res = self.ev(x, ctx, fm, env, S)
+                elif c is not False:
+                    res = self.mux(c, self.ev(x, ctx, fm, env, S), res)
+            return res
         if k == "quant":
             if e[1] == "E":
                 return self.exists_bool(e[2], e[3], ctx, fm, env, S)
@@ -1248,6 +1275,14 @@ class Lowerer:
             if v is not None and v not in st1:
                 rhs = self.ev(e[3], ctx, fm, self.with_next(env, st1))
                 self.gen_next(rest, {**st1, v: rhs}, label)
+                return
+        if k == "binop" and e[1] == "\\in" and e[2][0] == "prime":
+            # x' \in S: one successor per member of S (TLC enumerates S)
+            v = self.resolve_var(e[2][1], ctx, fm, env)
+            if v is not None and v not in st1:
+                dom = self.ev(e[3], ctx, fm, self.with_next(env, st1))
+                for g, x in self.distinct_items(dom):
+                    self.guarded(g, lambda x=x: self.gen_next(rest, {**st1, v: x}, label))
                 return
         if k == "unchanged":
             new1, conds = st1, []

@@ -189,6 +189,43 @@ class TInt(Ty):
         return SInt(f"((int){code} + {self.lo})" if self.lo else f"(int){code}", self.lo, self.hi)
 
 
+class TBool(Ty):
+    """BOOLEAN-valued field: one bit."""
+
+    def __init__(self):
+        self.card = 2
+        self.atom = None
+
+    def kind(self):
+        return "bool"
+
+    def describe(self):
+        return {"t": "bool"}
+
+    def alloc(self, lay, path):
+        self._alloc_scalar(lay, path)
+
+    def py_enc(self, v):
+        if not isinstance(v, bool):
+            raise LowerError(f"value {fmt(v)} is not a boolean")
+        return 1 if v else 0
+
+    def py_dec(self, code):
+        return bool(code)
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            return lw.enc_union_into(self, v)
+        if not isinstance(v, SBool):
+            raise LowerError(f"cannot store {v!r} in a boolean field")
+        return lw.tmp_int(f"({v.s} ? 1 : 0)")
+
+    def dec(self, lw, code):
+        return SBool(f"({code} != 0)")
+
+
 class TEnum(Ty):
     def __init__(self, atoms: list, gids: dict):
         self.atoms = sorted(atoms, key=lambda a: gids[a])

@@ -88,11 +88,14 @@ class TypeInference:
             raise LowerError(f"layout type is not a constant set: {v!r}")
         if not v:
             raise LowerError("empty set used as a layout type")
+        bools = [x for x in v if isinstance(x, bool)]
         ints = [x for x in v if is_int_const(x)]
         atoms = [x for x in v if is_atom_const(x)]
         recs = [x for x in v if isinstance(x, FnVal)]
         sets = [x for x in v if isinstance(x, frozenset)]
         parts: list[L.Ty] = []
+        if bools:
+            parts.append(L.TBool())
         if ints:
             parts.append(L.TInt(min(ints), max(ints)))
         if atoms:
@@ -111,7 +114,7 @@ class TypeInference:
         if sets:
             universe = frozenset().union(*sets)
             parts.append(L.TSet(self.type_from_setval(universe)))
-        if len(ints) + len(atoms) + len(recs) + len(sets) != len(v):
+        if len(bools) + len(ints) + len(atoms) + len(recs) + len(sets) != len(v):
             raise LowerError("unsupported element kind in a layout type")
         return parts[0] if len(parts) == 1 else L.TUnion(sorted(parts, key=lambda t: t.kind()))
 

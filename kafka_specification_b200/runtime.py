@@ -155,6 +155,8 @@ class StateDecoder:
         k = t["t"]
         if k == "int":
             return t["hi"] - t["lo"] + 1
+        if k == "bool":
+            return 2
         if k == "enum":
             return len(t["values"])
         if k == "rec":
@@ -174,6 +176,8 @@ class StateDecoder:
         k = t["t"]
         if k == "int":
             return code + t["lo"]
+        if k == "bool":
+            return bool(code)
         if k == "enum":
             return _parse_atom(t["values"][code])
         if k == "rec":

@@ -348,6 +348,8 @@ class Interp:
         if k == "app" or k == "inst":
             op = self.find_operator(e, ctx, fm, env)
             if op is None:
+                if k == "app" and e[1] == "Cardinality" and len(e[2]) == 1:
+                    return len(set_elems(self.ev(e[2][0], ctx, fm, env, st, st1)))
                 if k == "app" and e[1] == "Permutations" and len(e[2]) == 1:
                     # TLC module: the set of all permutations (bijections S -> S) of a finite set
                     elems = sorted(set_elems(self.ev(e[2][0], ctx, fm, env, st, st1)), key=sort_key)
@@ -387,6 +389,13 @@ class Interp:
             return self.ev(e[3], ctx, fm, env, st, st1)
         if k == "let":
             return self.ev(e[2], ctx, fm, self.let_env(e[1], ctx, fm, env), st, st1)
+        if k == "case":
+            for g, x in e[1]:
+                if self.ev_bool(g, ctx, fm, env, st, st1):
+                    return self.ev(x, ctx, fm, env, st, st1)
+            if e[2] is None:
+                raise EvalError("CASE: no arm applies and there is no OTHER")
+            return self.ev(e[2], ctx, fm, env, st, st1)
         if k == "quant":
             is_exists = e[1] == "E"
             for env2 in self.bindings(e[2], ctx, fm, env, st, st1):
