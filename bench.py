@@ -120,6 +120,8 @@ def cpu_sample(model: str, seconds_budget: float = 20.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kso
     reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
+    if "kso" not in reg:
+        return None
     kmodel, params = reg["kso"]
     cores = os.cpu_count() or 1
     best_t, best_rate = cores, 0.0
@@ -142,7 +144,7 @@ def cpu_sample(model: str, seconds_budget: float = 20.0):
 def config_for(model: str, extra: dict | None = None) -> dict:
     reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
     c = {"workload": f"{reg['module']} ({reg['cfg']}): full BFS, KafkaReplication.tla 3 brokers LogSize 4, "
-                     f"kso params {reg['kso'][1]}",
+                     f"kso params {(reg.get('kso') or [None, None])[1]}",
          "model": model, "l2": "inputs larger than L2: hash set and state store are GBs and the set is reset every step"}
     if extra:
         c.update(extra)

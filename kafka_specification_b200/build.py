@@ -38,7 +38,7 @@ def tla_search_dirs() -> list[str]:
     env = os.environ.get("KSPEC_TLA_PATH")
     if env:
         dirs += env.split(os.pathsep)
-    dirs += ["/root/reference", MODELS_DIR]
+    dirs += ["/root/reference", MODELS_DIR, os.path.join(ROOT, "tests", "specs")]
     return [d for d in dirs if os.path.isdir(d)]
 
 

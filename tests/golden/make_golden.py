@@ -58,14 +58,21 @@ def main():
             continue                    # minutes of CPU and tens of GB: only when asked for by name
         cfg_text = open(os.path.join(ROOT, spec["cfg"])).read()
         cfg = parse_cfg(cfg_text)
-        model, params = spec["kso"]
         t0 = time.time()
-        b = kso.run(model, params, max_states=spec.get("max_states", 4_000_000), invariants=cfg.invariants,
-                    symmetry=bool(spec.get("symmetry")))
-        g = {"module": spec["module"], "cfg": spec["cfg"], "kso": spec["kso"], "symmetry": bool(spec.get("symmetry")),
+        dirs = ["/root/reference", os.path.join(ROOT, "models"), os.path.join(ROOT, "tests", "specs")]
+        if "kso" in spec:
+            model, params = spec["kso"]
+            b = kso.run(model, params, max_states=spec.get("max_states", 4_000_000), invariants=cfg.invariants,
+                        symmetry=bool(spec.get("symmetry")))
+            src = ["oracle_b"]
+        else:
+            # a spec Oracle B has no hand-written restatement of (synthetic front-end tests): Oracle A alone
+            b = tla_interp.run_bfs(spec["module"], dirs, cfg_text + "\nCHECK_DEADLOCK FALSE\n", stop_on_violation=False)
+            src = []
+        g = {"module": spec["module"], "cfg": spec["cfg"], "kso": spec.get("kso"), "symmetry": bool(spec.get("symmetry")),
              "distinct": b["distinct"], "generated": b["generated"], "depth": b["depth"], "levels": b["levels"],
              "deadlocks": b["deadlocks"], "first_violation_level": b["first_violation_level"],
-             "check_deadlock": cfg.check_deadlock, "sources": ["oracle_b"]}
+             "check_deadlock": cfg.check_deadlock, "sources": src}
         cf = closed_form(spec["module"], cfg)
         for k, v in cf.items():
             assert g[k] == v, (name, k, g[k], v)
@@ -74,12 +81,11 @@ def main():
         if spec.get("oracle_a"):
             # full-space statistics: never stop at a violation, deadlock checking off
             stats_cfg = cfg_text + "\nCHECK_DEADLOCK FALSE\n"
-            a = tla_interp.run_bfs(spec["module"], ["/root/reference", os.path.join(ROOT, "models")], stats_cfg,
-                                   collect_states=True, stop_on_violation=False)
+            a = tla_interp.run_bfs(spec["module"], dirs, stats_cfg, collect_states=True, stop_on_violation=False)
             for k in ("distinct", "generated", "depth", "levels", "deadlocks"):
                 assert a[k] == g[k], (name, k, a[k], g[k])
             for inv, lvl in b["first_violation_level"].items():
-                assert a["first_violation_level"][inv] == lvl, (name, inv, a["first_violation_level"], lvl)
+                assert a["first_violation_level"].get(inv) == lvl, (name, inv, a["first_violation_level"], lvl)
             g["first_violation_level"] = a["first_violation_level"]     # includes TypeOk
             if not spec.get("symmetry"):       # under SYMMETRY the choice of orbit representatives is free
                 g["state_digest"] = state_digest(a["states"])

@@ -21,8 +21,8 @@ def test_closed_forms_oracle_b():
 
 def test_oracle_b_matches_goldens(goldens):
     for name, g in goldens.items():
-        if g["distinct"] > 3_000_000:
-            continue                      # the headline configs take minutes and tens of GB on the CPU
+        if g["distinct"] > 3_000_000 or not g.get("kso"):
+            continue                      # headline configs: minutes and tens of GB; synthetic specs: no C restatement
         model, params = g["kso"]
         invs = [i for i in g["first_violation_level"] if i != "TypeOk"]
         r = kso.run(model, params, max_states=4_000_000, invariants=invs, symmetry=bool(g.get("symmetry")))
