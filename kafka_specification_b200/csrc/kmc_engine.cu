@@ -5,18 +5,23 @@
 //
 // It replaces TLC's Worker next-state loop, FPSet and StateQueue:
 //
-//   k_expand  (K1)  one thread per frontier state: coalesced load of the packed state vector,
-//                   the lowered Next switch table (kmc_model::expand), one candidate row
-//                   (state words + parent/action word) per successor, bucketed by owner rank
-//                   = fingerprint high bits.  Row slots are claimed with warp-aggregated
-//                   atomics (one atomic per warp per emit site).
-//   k_insert  (K2)  one thread per candidate: 64-bit fingerprint, open-addressing hash set in
-//                   HBM with 32-byte buckets (4 fingerprints = one DRAM sector, read with two
-//                   128-bit loads), CAS insertion, warp ballot/popc compaction of the winners
-//                   into the state store (= next frontier), parent link, and (K3) invariant
-//                   evaluation on every new state and on every constraint-violating successor.
-//                   Violating states (rare, terminal) go to a small ring; the host reports the
-//                   one with the smallest fingerprint, so the counterexample is deterministic.
+//   k_expand  (K1)  lowered Next over the frontier.  The unrolled Next is hundreds of KB of SASS, so it
+//                   is cut into NUM_GROUPS groups; one 1024-thread CTA per SM sweeps one group at a
+//                   time over a tile of states (all warps in the same group => the group's code stays in
+//                   the instruction cache).  Successor rows (state words + parent/action word) are
+//                   staged per warp in shared memory and flushed in bulk: into the local candidate
+//                   buffer (one rank), into per-owner regions (NCCL exchange), or -- fused exchange --
+//                   straight into the owner rank's inbox through a CUDA-IPC peer mapping (NVLink stores).
+//   k_insert  (K2)  one thread per candidate: 64-bit fingerprint (of the orbit representative under
+//                   SYMMETRY), open-addressing hash set in HBM with 32-byte buckets (4 fingerprints =
+//                   one DRAM sector, two 128-bit loads), CAS insertion, warp ballot/popc compaction of
+//                   the winners into the state store (= next frontier), parent link.  k_insert_inbox is
+//                   the same over the regions the peers filled.
+//   k_invariants (K3) the cfg's INVARIANTs on the new states of a level (compacted => every lane busy).
+//                   Violating states (rare, terminal) go to a small ring; the host reports the one with
+//                   the smallest fingerprint, so the counterexample is deterministic.
+//   k_expand2       opt-in two-phase form of K1 (guard masks, CTA-wide compaction, bodies); measured
+//                   slower, see DESIGN.md section 4.
 //
 // HBM layout (per rank):   table  u64[2^table_log2]            fingerprints, 0 = empty
 //                          store  u64[max_states][W]           all distinct states, BFS order;
