@@ -443,12 +443,30 @@ __device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
   for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
 }
 
+// Diagnostic build (-DKMC_GROUP_CLOCKS, tools/group_clocks.py): SM cycles each group holds a CTA, summed over
+// CTAs and tiles.  The stamp is taken by thread 0 right after the CTA-wide barrier that opens a group, so the
+// difference of two stamps is the time the slowest warp needed for the group in between (flushes included).
+#ifdef KMC_GROUP_CLOCKS
+__device__ unsigned long long g_group_clocks[M::NUM_GROUPS + 1];
+__device__ __forceinline__ void group_tick(int g) {
+  __shared__ long long t_last;
+  if (threadIdx.x == 0) {
+    long long t = clock64();
+    if (g > 0) atomicAdd(&g_group_clocks[g - 1], (unsigned long long)(t - t_last));
+    t_last = t;
+  }
+}
+#endif
+
 template <int G, bool MULTI, bool FUSED>
 struct GroupRunner {
   static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
                                               int spt, unsigned* nsucc, int& failed, uint64_t* wbuf, unsigned* wcnt,
                                               ExpandStats& xs) {
     __syncthreads();
+#ifdef KMC_GROUP_CLOCKS
+    group_tick(G);
+#endif
 #pragma unroll 1
     for (int j = 0; j < spt; ++j) {
       uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
@@ -468,7 +486,12 @@ struct GroupRunner {
 template <bool MULTI, bool FUSED>
 struct GroupRunner<M::NUM_GROUPS, MULTI, FUSED> {
   static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&,
-                                              uint64_t*, unsigned*, ExpandStats&) {}
+                                              uint64_t*, unsigned*, ExpandStats&) {
+#ifdef KMC_GROUP_CLOCKS
+    __syncthreads();
+    group_tick(M::NUM_GROUPS);
+#endif
+  }
 };
 
 // ----------------------------------------------------------------------------------------
@@ -1481,6 +1504,22 @@ int kmcm_action_counts(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) 
   *n = std::min<size_t>(M::NUM_ACTIONS, E.action_counts.size());
   for (size_t i = 0; i < *n && i < cap; ++i) out[i] = E.action_counts[i];
   return KMC_OK;
+}
+
+// Diagnostic, not part of include/kspecmc.h: per-group SM cycles of K1 (all zero unless built with
+// -DKMC_GROUP_CLOCKS).  *n = number of groups.
+int kmcm_group_clocks(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) {
+  if (!c || !n) return KMC_E_BADARG;
+  *n = (size_t)M::NUM_GROUPS;
+#ifdef KMC_GROUP_CLOCKS
+  unsigned long long h[M::NUM_GROUPS + 1];
+  if (cudaMemcpyFromSymbol(h, g_group_clocks, sizeof(h)) != cudaSuccess) return KMC_E_CUDA;
+  for (size_t i = 0; i < *n && i < cap; ++i) out[i] = h[i];
+  return KMC_OK;
+#else
+  for (size_t i = 0; i < *n && i < cap; ++i) out[i] = 0;
+  return KMC_E_STATE;
+#endif
 }
 
 int kmcm_violation(const kmcm_ctx* c, kmc_violation_t* out) {
