@@ -77,6 +77,7 @@ typedef struct {
   uint64_t max_states;      /* state-store capacity                                       */
   uint64_t complete;        /* 1 if the search ran to an empty queue                      */
   double gpu_ms_invariant;  /* sum over invariant-kernel launches (counted in launches_other) */
+  uint64_t dcache_hits;     /* candidates the L2-resident duplicate filter answered (no DRAM probe) */
 } kmc_stats_t;
 
 typedef struct {
@@ -104,11 +105,11 @@ typedef struct {
  * `python -m kafka_specification_b200.build`).  options_json: flat JSON object, all keys
  * optional: "device":0, "table_log2":27, "max_states":N, "cand_bytes":N, "rank":0, "world":1,
  * "continue":false, "check_deadlock":true|false (override), "timing":true,
- * "fused":false (single GPU: insert from the expand kernel's staged flush; measured slower),
  * "stop_after_states":N (bounded run: stop at the first level end holding >= N states),
  * "stream":H (cudaStream_t handle of the caller to launch on instead of a private stream),
  * "fanout_bound":K (successors per state assumed when sizing frontier chunks; default min(MAX_FANOUT, 32)),
- * "two_phase":false (guard phase + compacted body phase variant of the expand kernel).            */
+ * "dcache_log2":L (L2-resident duplicate filter of 2^L recently confirmed fingerprints in front of the set; 0 = off),
+ * "one_phase":false (comparison only: the round-1 one-phase expand kernel; needs a -DKMC_ONE_PHASE library).  */
 int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out);
 void kmc_destroy(kmc_ctx* ctx);
 int kmc_model_info(const kmc_ctx* ctx, kmc_model_info_t* out);

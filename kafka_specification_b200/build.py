@@ -74,8 +74,17 @@ def model_dir(name: str) -> str:
     return os.path.join(BUILD, "models", name)
 
 
-def model_lib_path(name: str) -> str:
-    return os.path.join(model_dir(name), f"libkmc_{name}.so")
+# build variants: extra nvcc flags and a library-name suffix.  The default build carries the two-phase expand
+# kernel only (-DKMC_NO_ONE_PHASE drops the one-phase form of the lowered Next from the translation unit);
+# "1p" adds the round-1 one-phase kernel for A/B measurements (option "one_phase": true).
+VARIANTS = {
+    "": ["-DKMC_NO_ONE_PHASE"],
+    "1p": ["-DKMC_ONE_PHASE"],
+}
+
+
+def model_lib_path(name: str, variant: str = "") -> str:
+    return os.path.join(model_dir(name), f"libkmc_{name}{'.' + variant if variant else ''}.so")
 
 
 def _engine_stamp() -> str:
@@ -106,21 +115,26 @@ def lower_to_dir(module: str, cfg_path: str, name: str):
     return m
 
 
-def compile_model(name: str, force: bool = False, verbose_ptxas: bool = True) -> str:
+def compile_model(name: str, force: bool = False, verbose_ptxas: bool = True, variant: str = "",
+                  extra_flags: list[str] | None = None) -> str:
     d = model_dir(name)
     hdr = os.path.join(d, "model.h")
-    so = model_lib_path(name)
-    stamp_file = os.path.join(d, "build.stamp")
+    so = model_lib_path(name, variant)
+    stamp_file = os.path.join(d, f"build{'.' + variant if variant else ''}.stamp")
     with open(hdr, "rb") as f:
         stamp = hashlib.sha256(f.read()).hexdigest()[:16] + ":" + _engine_stamp()
     if not force and os.path.exists(so) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return so
     cmd = [nvcc_path(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-           "-diag-suppress", "177",
+           "-diag-suppress", "177", *VARIANTS[variant], *(extra_flags or []),
            f"-I{INCLUDE}", "-include", hdr, os.path.join(CSRC, "kmc_engine.cu"), "-o", so]
     if verbose_ptxas:
         cmd[1:1] = ["-Xptxas", "-v"]
-    _run(cmd, log=os.path.join(d, "nvcc.log"))
+    import time
+    t0 = time.time()
+    _run(cmd, log=os.path.join(d, f"nvcc{'.' + variant if variant else ''}.log"))
+    with open(os.path.join(d, f"nvcc{'.' + variant if variant else ''}.log"), "a") as f:
+        f.write(f"nvcc wall time: {time.time() - t0:.1f} s\n")
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return so

@@ -54,6 +54,7 @@ static constexpr int MAX_WORLD = 8;
 static constexpr uint64_t NO_PARENT = 0x0000FFFFFFFFFFFFull;
 static constexpr uint64_t IDX_MASK = 0x000000FFFFFFFFFFull;
 static constexpr bool EXACT64 = (M::STATE_BITS <= 63);
+static_assert(M::NUM_ACTIONS <= 255, "the parent word holds the action id in 8 bits");
 
 #define KMC_FAIL_TABLE_FULL 2
 #define KMC_FAIL_STORE_FULL 3
@@ -114,6 +115,7 @@ struct DevCounters {
   unsigned long long fail;
   unsigned long long max_fanout_seen;
   unsigned long long viol_count;         // rows claimed in the violator ring
+  unsigned long long dcache_hits;        // candidates recognised as duplicates by the L2-resident filter
   unsigned long long action_counts[64];
 };
 
@@ -137,6 +139,11 @@ struct Params {
   uint32_t rank, world;
   uint32_t check_deadlock;
   uint32_t count_actions;
+  // duplicate filter in front of the set: a direct-mapped array of recently confirmed fingerprints, small enough
+  // to stay in L2 (pinned there with an access-policy window).  A hit proves the fingerprint is in the set (an
+  // entry is only written after the set held it), so the duplicate costs no DRAM probe; a miss costs one L2 read.
+  uint64_t* dcache;
+  uint32_t dcache_shift;    // 64 - log2(entries); 0 = filter off
   // fused exchange (world > 1, after kmc_shard_open_peers): every rank's inbox, mapped into this
   // process through CUDA IPC.  An inbox is two buffers (double buffering); a buffer is an 8-word
   // header (rows sent by each source rank) followed by world regions of region_rows rows.
@@ -234,7 +241,10 @@ struct Prefetched {
   uint64_t fp;
   ulonglong2 lo, hi;
   bool inmodel;
+  bool cached;      // duplicate filter hit: the fingerprint is known to be in the set
 };
+
+__device__ __forceinline__ uint64_t dcache_slot(uint64_t fp, uint32_t shift) { return (fp * 0x9E3779B97F4A7C15ull) >> shift; }
 
 // first half of an insert: fingerprint + issue the bucket loads (no dependent use yet)
 __device__ __forceinline__ Prefetched prefetch_row(const Params& p, const State& s, bool valid) {
@@ -242,28 +252,41 @@ __device__ __forceinline__ Prefetched prefetch_row(const Params& p, const State&
   f.fp = 0;
   f.lo = f.hi = make_ulonglong2(0, 0);
   f.inmodel = false;
+  f.cached = false;
   if (valid) {
     f.inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
     f.fp = state_fp(s);
     if (f.inmodel) {
-      const uint64_t* base = p.table + (bucket_of(f.fp, p.bucket_mask) << 2);
-      f.lo = ld_bucket_half(base);
-      f.hi = ld_bucket_half(base + 2);
+      if (p.dcache_shift) {
+        uint64_t c;
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(c) : "l"(p.dcache + dcache_slot(f.fp, p.dcache_shift)));
+        f.cached = (c == f.fp);
+      }
+      if (!f.cached) {
+        const uint64_t* base = p.table + (bucket_of(f.fp, p.bucket_mask) << 2);
+        f.lo = ld_bucket_half(base);
+        f.hi = ld_bucket_half(base + 2);
+      }
     }
   }
   return f;
 }
 
 __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint64_t meta, bool valid, const Prefetched& f,
-                                            unsigned& probes, unsigned& oom, int& failed) {
+                                            unsigned& probes, unsigned& oom, unsigned& hits, int& failed) {
   bool is_new = false;
   if (valid) {
     const bool inmodel = f.inmodel;
     const uint64_t fp = f.fp;
     if (inmodel) {
-      int r = fpset_insert_pre(p.table, p.bucket_mask, fp, f.lo, f.hi, probes);
-      if (r < 0) failed = KMC_FAIL_TABLE_FULL;
-      is_new = r > 0;
+      if (f.cached) {
+        ++hits;
+      } else {
+        int r = fpset_insert_pre(p.table, p.bucket_mask, fp, f.lo, f.hi, probes);
+        if (r < 0) failed = KMC_FAIL_TABLE_FULL;
+        is_new = r > 0;
+        if (p.dcache_shift && r >= 0) p.dcache[dcache_slot(fp, p.dcache_shift)] = fp;
+      }
     } else {
       ++oom;
       // TLC also checks invariants on successors discarded by a CONSTRAINT; they are not stored,
@@ -295,22 +318,41 @@ __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// K1: expand
+// ----------------------------------------------------------------------------------------
 // Successor rows are staged per warp in shared memory and flushed in bulk: one global slot claim
 // per flush (instead of one ~600-cycle atomic round trip per emit site), coalesced row stores,
 // and -- multi-rank -- the owner computation (a fingerprint) done with all 32 lanes busy instead
-// of inside the divergent emit site.
-static constexpr int STAGE_ROWS = (ROW <= 5) ? 96 : (ROW <= 8 ? 64 : 40);   // rows per warp (<= 200 KB per 1024-thread CTA)
-static constexpr int STAGE_FLUSH = STAGE_ROWS / 2;                          // flush once at least this many rows are staged
+// of inside the emit site.  The stage is addressed through 32-bit shared-window addresses and
+// st.shared / atom.shared so that no generic-address store (ST + QSPC) is ever generated.
+#ifndef EXPAND_BLOCK_THREADS
+#define EXPAND_BLOCK_THREADS 1024
+#endif
+static constexpr int EXPAND_BLOCK = EXPAND_BLOCK_THREADS;
+static constexpr int NWARPS = EXPAND_BLOCK / 32;
+static constexpr int STAGE_ROWS = 64;            // rows per warp; a body pass adds <= 32, a flush empties it
+static constexpr int STAGE_FLUSH = 32;           // flush once at least this many rows are staged
+static constexpr int LIST_CAP = 12288;           // (state, site) pairs of one scatter round, 16-bit tile slots
+static constexpr int MAX_GROUP_SITES = 64;
 
-template <bool MULTI>
-__device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t* words, uint64_t meta, bool valid,
-                                                 int& failed) {
-  // one row per lane (valid lanes only), slot claims aggregated per owner
-  State s;
-#pragma unroll
-  for (int i = 0; i < W; ++i) s.w[i] = words[i];
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned atoms_add(uint32_t a, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+
+// one row per lane (valid lanes only) into the owner's region, slot claims aggregated per owner
+__device__ __forceinline__ void claim_and_store(const Params& p, const State& s, uint64_t meta, bool valid, int& failed) {
   uint32_t dest = 0xFFu;
-  if (valid) dest = MULTI ? owner_of(state_fp(s), p.world) : 0u;
+  if (valid) dest = owner_of(state_fp(s), p.world);
   unsigned peers = __match_any_sync(0xffffffffu, dest);
   unsigned lane = lane_id();
   int leader = __ffs(peers) - 1;
@@ -334,33 +376,14 @@ __device__ __forceinline__ void claim_and_store(const Params& p, const uint64_t*
 }
 
 // called by all 32 lanes of a warp at a converged point
-struct ExpandStats {
-  unsigned probes, oom;
-};
-
-template <bool MULTI, bool FUSED>
-__device__ __forceinline__ void flush_stage(const Params& p, uint64_t* wbuf, unsigned* wcnt, bool force, int& failed,
-                                             ExpandStats& xs) {
+__device__ __forceinline__ void flush_stage(const Params& p, uint32_t wbuf, uint32_t wcnt, bool force, int& failed) {
   __syncwarp();
-  unsigned n = *wcnt;
+  unsigned n;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(wcnt));
   if (n > (unsigned)STAGE_ROWS) n = STAGE_ROWS;
   if (n == 0 || (!force && n < (unsigned)STAGE_FLUSH)) return;
   unsigned lane = lane_id();
-  if (FUSED) {
-    // single GPU: the staged rows never go to HBM -- fingerprint, probe and insert them right
-    // here, 32 at a time with every lane busy.  The probe's DRAM latency overlaps the integer work
-    // of the CTA's other warps.
-    for (unsigned r0 = 0; r0 < n; r0 += 32) {
-      unsigned r = r0 + lane;
-      bool valid = r < n;
-      State s;
-      const uint64_t* row = wbuf + (valid ? r : 0) * ROW;
-#pragma unroll
-      for (int k = 0; k < W; ++k) s.w[k] = row[k];
-      Prefetched f = prefetch_row(p, s, valid);
-      insert_row(p, s, row[W], valid, f, xs.probes, xs.oom, failed);
-    }
-  } else if (!MULTI) {
+  if (p.world == 1) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&p.ctr->cand_count[0], (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -368,29 +391,39 @@ __device__ __forceinline__ void flush_stage(const Params& p, uint64_t* wbuf, uns
       failed = KMC_FAIL_CAND_FULL;
     } else {
       uint64_t* dst = p.cand + base * ROW;
-      for (unsigned k = lane; k < n * ROW; k += 32) dst[k] = wbuf[k];      // coalesced
+      for (unsigned k = lane; k < n * ROW; k += 32) dst[k] = lds64(wbuf + k * 8);      // coalesced
     }
   } else {
     for (unsigned r0 = 0; r0 < n; r0 += 32) {
       unsigned r = r0 + lane;
       bool valid = r < n;
-      const uint64_t* row = wbuf + (valid ? r : 0) * ROW;
-      claim_and_store<true>(p, row, row[W], valid, failed);
+      State s;
+      const uint32_t row = wbuf + (valid ? r : 0) * (ROW * 8);
+#pragma unroll
+      for (int k = 0; k < W; ++k) s.w[k] = lds64(row + k * 8);
+      claim_and_store(p, s, lds64(row + W * 8), valid, failed);
     }
   }
   __syncwarp();
-  if (lane == 0) *wcnt = 0;
+  if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wcnt), "r"(0u) : "memory");
   __syncwarp();
 }
 
-template <bool MULTI>
+// The sink handed to the lowered bodies.  It holds values only (no reference to the kernel parameters and no
+// out-of-line member): anything that makes the object addressable sends it -- and every pointer in it --
+// through local memory and turns the stage stores / counter atomics into generic-address operations.
 struct CandSink {
-  const Params& p;
   uint64_t parent_ref;
-  uint64_t* wbuf;      // this warp's staging rows (shared memory)
-  unsigned* wcnt;      // rows staged by this warp
+  uint32_t wbuf;       // this warp's staging rows (shared-window address)
+  uint32_t wcnt;       // rows staged by this warp (shared-window address)
+  unsigned long long* action_counts;   // per-action counters (global memory), or nullptr
   int n;
   int failed;
+#ifdef KMC_ONE_PHASE
+  uint64_t* cand;                      // one-phase comparison kernel only (single rank): overflow rows go straight
+  unsigned long long* cand_count;      // to the candidate buffer
+  uint64_t region_rows;
+#endif
 
   __device__ __forceinline__ void emit(const State& s, int action) {
     ++n;
@@ -399,306 +432,285 @@ struct CandSink {
     unsigned lane = lane_id();
     int leader = __ffs(active) - 1;
     unsigned base = 0;
-    if ((int)lane == leader) base = atomicAdd(wcnt, (unsigned)__popc(active));      // shared-memory atomic
+    if ((int)lane == leader) base = atoms_add(wcnt, (unsigned)__popc(active));
     base = __shfl_sync(active, base, leader);
     unsigned pos = base + __popc(active & ((1u << lane) - 1));
     if (pos < (unsigned)STAGE_ROWS) {
-      uint64_t* row = wbuf + pos * ROW;
+      const uint32_t row = wbuf + pos * (ROW * 8);
 #pragma unroll
-      for (int i = 0; i < W; ++i) row[i] = s.w[i];
-      row[W] = meta;
+      for (int i = 0; i < W; ++i) sts64(row + i * 8, s.w[i]);
+      sts64(row + W * 8, meta);
     } else {
-      // staging area full (rare burst): straight to global memory, one claim per lane group
-      uint32_t dest = MULTI ? owner_of(state_fp(s), p.world) : 0u;
-      unsigned long long gpos = atomicAdd(&p.ctr->cand_count[dest], 1ull);
-      if (gpos >= p.region_rows) {
-        failed = KMC_FAIL_CAND_FULL;
-      } else {
-        uint64_t* row = p.p2p ? p.peer_inbox[dest] + (uint64_t)p.inbox_buf * p.inbox_stride + INBOX_HEADER +
-                                    ((uint64_t)p.rank * p.region_rows + gpos) * ROW
-                              : p.cand + ((uint64_t)dest * p.region_rows + gpos) * ROW;
+#ifdef KMC_ONE_PHASE
+      if (cand != nullptr) {           // one-phase kernel: a burst of emits between two flushes
+        unsigned long long gpos = atomicAdd(cand_count, 1ull);
+        if (gpos >= region_rows) {
+          failed = KMC_FAIL_CAND_FULL;
+        } else {
+          uint64_t* grow = cand + gpos * ROW;
 #pragma unroll
-        for (int i = 0; i < W; ++i) row[i] = s.w[i];
-        row[W] = meta;
-      }
+          for (int i = 0; i < W; ++i) grow[i] = s.w[i];
+          grow[W] = meta;
+        }
+      } else
+#endif
+      // two-phase kernel: cannot happen (a body pass adds <= 32 rows to a stage that is flushed at >= STAGE_FLUSH)
+      failed = KMC_FAIL_CAND_FULL;
     }
-    if (p.count_actions && action < 64) atomicAdd(&p.ctr->action_counts[action], 1ull);
+    if (action_counts != nullptr && action < 64) atomicAdd(action_counts + action, 1ull);
   }
   __device__ __forceinline__ void fail(int code) { failed = code; }
 };
-
-// The lowered Next is hundreds of KB of straight-line SASS -- far beyond the SM's instruction
-// caches.  expand() is therefore cut (by the lowering) into NUM_GROUPS groups of ~1k instructions,
-// and the whole CTA sweeps ONE group at a time over a tile of EXPAND_BLOCK x spt states
-// (__syncthreads between groups keeps all 16 warps of the SM in the same group), so every fetched
-// instruction line serves 16 warps x spt states instead of one warp once.
-#ifndef EXPAND_BLOCK_THREADS
-#define EXPAND_BLOCK_THREADS 1024
-#endif
-static constexpr int EXPAND_BLOCK = EXPAND_BLOCK_THREADS;
-#ifndef EXPAND_SPT_MAX
-#define EXPAND_SPT_MAX 4
-#endif
-static constexpr int EXPAND_SPT = EXPAND_SPT_MAX;
 
 __device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
 #pragma unroll
   for (int k = 0; k < W; ++k) s.w[k] = __ldg(src + k);
 }
 
-// Diagnostic build (-DKMC_GROUP_CLOCKS, tools/group_clocks.py): SM cycles each group holds a CTA, summed over
-// CTAs and tiles.  The stamp is taken by thread 0 right after the CTA-wide barrier that opens a group, so the
-// difference of two stamps is the time the slowest warp needed for the group in between (flushes included).
-#ifdef KMC_GROUP_CLOCKS
-__device__ unsigned long long g_group_clocks[M::NUM_GROUPS + 1];
-__device__ __forceinline__ void group_tick(int g) {
-  __shared__ long long t_last;
-  if (threadIdx.x == 0) {
-    long long t = clock64();
-    if (g > 0) atomicAdd(&g_group_clocks[g - 1], (unsigned long long)(t - t_last));
-    t_last = t;
-  }
-}
-#endif
-
-template <int G, bool MULTI, bool FUSED>
-struct GroupRunner {
-  static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
-                                              int spt, unsigned* nsucc, int& failed, uint64_t* wbuf, unsigned* wcnt,
-                                              ExpandStats& xs) {
-    __syncthreads();
-#ifdef KMC_GROUP_CLOCKS
-    group_tick(G);
-#endif
-#pragma unroll 1
-    for (int j = 0; j < spt; ++j) {
-      uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
-      if (i < count) {
-        State s;
-        load_state(s, p.store + (first + i) * W);
-        CandSink<MULTI> sink{p, (first + i) | ((uint64_t)p.rank << 40), wbuf, wcnt, 0, 0};
-        M::expand_group(M::GroupTag<G>{}, s, sink);
-        nsucc[j] += (unsigned)sink.n;
-        failed |= sink.failed;
-      }
-      flush_stage<MULTI, FUSED>(p, wbuf, wcnt, false, failed, xs);
-    }
-    GroupRunner<G + 1, MULTI, FUSED>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt, xs);
-  }
-};
-template <bool MULTI, bool FUSED>
-struct GroupRunner<M::NUM_GROUPS, MULTI, FUSED> {
-  static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned*, int&,
-                                              uint64_t*, unsigned*, ExpandStats&) {
-#ifdef KMC_GROUP_CLOCKS
-    __syncthreads();
-    group_tick(M::NUM_GROUPS);
-#endif
-  }
-};
-
 // ----------------------------------------------------------------------------------------
-// K1, two-phase form.  ncu's source page showed that 52 % of the instructions the one-phase kernel
-// issues run with <= 3 active lanes: they sit inside action bodies that only a few of a warp's 32
-// states enable.  Here every group is processed in two phases:
-//   A  all lanes evaluate item_guard (the cheap leading guards of each top-level block) on their own
-//      states; enabled (item, state) pairs are appended to a CTA-wide list in shared memory
-//      (ballot + one shared-memory atomic per warp);
-//   B  the list -- nearly sorted by item, because the CTA walks the items in lockstep -- is consumed
-//      32 entries at a time: each lane loads "its" state and runs item_body, so the expensive
-//      successor construction runs with (almost) all lanes on (almost) the same code.
+// K1, two-phase.  The round-1 kernel ran every thread through the whole lowered Next of its own
+// states: ncu showed 12 of 32 lanes per issued instruction, because an action body is enabled for
+// a few per cent of the states of a warp.  Here the lowering provides, per site group (<= 64 emit
+// sites), site_mask(s) = the COMPLETE path condition of every site (cheap compares, evaluated by
+// all lanes on their own states) and site_body<i>(s) = the straight-line successor construction.
+// One 1024-thread CTA per SM works on a tile of EXPAND_BLOCK x SPT states held in shared memory:
+//   A1  every thread evaluates the group's masks for its SPT states; per-site totals via ballot/popc
+//       and one shared-memory atomic per warp and site                                  -- barrier --
+//   A2  every warp derives the same segment offsets from the totals (segments padded to 32) and
+//       scatters its enabled (site, tile slot) pairs into the sorted list                -- barrier --
+//   B   the list is consumed 32 entries at a time; a chunk belongs to exactly one site, so the body
+//       dispatch is warp-uniform and the body runs with (almost) all lanes on the same code.
+//       B of group g overlaps A1 of group g+1 (double-buffered totals): two barriers per group.
+// Successor counts per state (deadlock detection, "states generated") are popc(mask).
 // ----------------------------------------------------------------------------------------
-static constexpr int LIST_CAP = 16384;
-static constexpr int MAX_GROUP_ITEMS = 64;
+static constexpr int STAGE_BYTES = NWARPS * STAGE_ROWS * ROW * 8;
+static constexpr int FIXED_SMEM_BYTES = STAGE_BYTES + LIST_CAP * 2 + (3 * MAX_GROUP_SITES + NWARPS + 8) * 4;
+static constexpr int SPT_FIT = (227 * 1024 - 1024 - FIXED_SMEM_BYTES) / (EXPAND_BLOCK * W * 8);
+static constexpr int SPT = SPT_FIT > 4 ? 4 : SPT_FIT;
+static_assert(SPT >= 1, "state too wide for the expand kernel's shared-memory tile");
+static constexpr int TILE = EXPAND_BLOCK * SPT;
+static_assert(TILE <= LIST_CAP, "a site's segment (<= TILE pairs) must fit one scatter round");
+static constexpr size_t EXPAND_SMEM_BYTES = (size_t)TILE * W * 8 + FIXED_SMEM_BYTES;
 
-struct TwoPhaseCtx {
-  uint64_t first, tile_base, count;
-  int spt;
-  uint64_t* wbuf;
-  unsigned* wcnt;
-  unsigned* list;        // [LIST_CAP] entries: item-in-group << 16 | state slot in the tile
-  unsigned* list_count;
-  unsigned* succ;        // successors per tile state [EXPAND_BLOCK * EXPAND_SPT]
-  unsigned* item_cnt;    // [MAX_GROUP_ITEMS] enabled pairs per item, then running cursor
-  unsigned* item_off;    // [MAX_GROUP_ITEMS] start of each item's segment in the list
+struct TileCtx {
+  uint32_t tile;        // [TILE][W] states (shared-window addresses throughout)
+  uint32_t list;        // [LIST_CAP] u16 tile slots, per-site segments
+  uint32_t cnt;         // [2][MAX_GROUP_SITES] enabled pairs per site (double-buffered across groups)
+  uint32_t cur;         // [MAX_GROUP_SITES] scatter cursors
+  uint32_t wbuf, wcnt;
+  uint64_t first, tile_base;
+  unsigned nvalid;      // states in this tile
 };
 
-// Bodies are inlined into an if-chain; the opaque copy stops the compiler from hoisting every
-// body's unpacking above the chain (which overflows the 64-register budget of a 1024-thread CTA).
-template <int I, int END>
-struct ItemDispatch {
-  template <class Sink>
-  static __device__ __forceinline__ void run(int item, const State& s, Sink& sink) {
-    if (item == I) {
+template <int LO, int HI>
+struct SiteDispatch {
+  static __device__ __forceinline__ void run(int i, const State& s, CandSink& sink) {
+    if constexpr (HI - LO == 1) {
+      // the opaque copy keeps the compiler from hoisting every body's unpacking above the dispatch
       State t = s;
 #pragma unroll
       for (int k = 0; k < W; ++k) asm volatile("" : "+l"(t.w[k]));
-      M::item_body(M::ItemTag<I>{}, t, sink);
-      return;
+      M::site_body(M::SiteTag<LO>{}, t, sink);
+    } else {
+      constexpr int MID = (LO + HI) / 2;
+      if (i < MID) SiteDispatch<LO, MID>::run(i, s, sink);
+      else SiteDispatch<MID, HI>::run(i, s, sink);
     }
-    ItemDispatch<I + 1, END>::run(item, s, sink);
   }
 };
-template <int END>
-struct ItemDispatch<END, END> {
-  template <class Sink>
-  static __device__ __forceinline__ void run(int, const State&, Sink&) {}
-};
 
-template <int G, bool MULTI>
-struct GroupRunner2 {
-  static __device__ __forceinline__ void run(const Params& p, const TwoPhaseCtx& c, int& failed, ExpandStats& xs) {
-    constexpr int BEGIN = M::GROUP_ITEM_BEGIN[G];
-    constexpr int END = M::GROUP_ITEM_BEGIN[G + 1];
-    constexpr int NI = END - BEGIN;
-    static_assert(NI <= MAX_GROUP_ITEMS, "too many items in one group");
+__device__ __forceinline__ unsigned lds32(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <int G>
+struct SiteGroupRunner {
+  static __device__ __forceinline__ void run(const Params& p, const TileCtx& c, unsigned (&nsucc)[SPT], int& failed) {
+    constexpr int BEGIN = M::SITE_GROUP_BEGIN[G];
+    constexpr int END = M::SITE_GROUP_BEGIN[G + 1];
+    constexpr int NS = END - BEGIN;
+    static_assert(NS >= 1 && NS <= MAX_GROUP_SITES, "site group size");
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
-    // ---- phase A1: guard masks (one unpack per state and group), count enabled pairs per item
-    uint64_t masks[EXPAND_SPT];
+    const uint32_t cnt = c.cnt + (G & 1) * (MAX_GROUP_SITES * 4);
+    // ---- A1: masks of this thread's states, per-site totals
+    uint64_t masks[SPT];
 #pragma unroll
-    for (int j = 0; j < EXPAND_SPT; ++j) {
+    for (int j = 0; j < SPT; ++j) {
+      const unsigned slot = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
       masks[j] = 0;
-      if (j < c.spt) {
-        const uint64_t i = c.tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
-        if (i < c.count) {
-          State s;
-          load_state(s, p.store + (c.first + i) * W);
-          masks[j] = M::group_guard_mask(M::GroupTag<G>{}, s);
-        }
+      if (slot < c.nvalid) {
+        State s;
+#pragma unroll
+        for (int k = 0; k < W; ++k) s.w[k] = lds64(c.tile + (slot * W + k) * 8);
+        masks[j] = M::site_mask(M::SiteGroupTag<G>{}, s);
+        nsucc[j] += (unsigned)__popcll(masks[j]);
       }
     }
 #pragma unroll 1
-    for (int k = 0; k < NI; ++k) {
+    for (int k = 0; k < NS; ++k) {
       unsigned n = 0;
 #pragma unroll
-      for (int j = 0; j < EXPAND_SPT; ++j) n += __popc(__ballot_sync(0xffffffffu, (masks[j] >> k) & 1));
-      if (lane == 0 && n) atomicAdd(&c.item_cnt[k], n);
+      for (int j = 0; j < SPT; ++j) n += __popc(__ballot_sync(0xffffffffu, (masks[j] >> k) & 1));
+      if (lane == 0 && n) atoms_add(cnt + k * 4, n);
     }
-    __syncthreads();
-    // ---- exclusive prefix over the (few) items
-    if (threadIdx.x == 0) {
-      unsigned run_total = 0;
-      for (int k = 0; k < NI; ++k) {
-        unsigned n = c.item_cnt[k];
-        c.item_off[k] = run_total;
-        c.item_cnt[k] = 0;               // becomes the running cursor of phase A2
-        run_total += n;
-      }
-      *c.list_count = run_total;
-    }
-    __syncthreads();
-    const unsigned total = *c.list_count;
-    if (total > (unsigned)LIST_CAP) {
-      // more enabled pairs than the list holds (a group in which nearly everything is enabled):
-      // run this group in one phase, every lane on its own states
-#pragma unroll 1
-      for (int j = 0; j < c.spt; ++j) {
-        const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
-        const uint64_t i = c.tile_base + loc;
-        if (i < c.count) {
-          State s;
-          load_state(s, p.store + (c.first + i) * W);
-          CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
-          M::expand_group(M::GroupTag<G>{}, s, sink);
-          if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
-          failed |= sink.failed;
-        }
-        flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
-      }
-    } else {
-      // ---- phase A2: scatter (item, state) pairs into per-item segments of the list
-#pragma unroll 1
-      for (int k = 0; k < NI; ++k) {
+    __syncthreads();                                   // totals complete; B of the previous group finished
+    // the other totals buffer (read last by B of group G-1) is cleared for A1 of group G+1
+    if (threadIdx.x < MAX_GROUP_SITES) sts32(c.cnt + ((G + 1) & 1) * (MAX_GROUP_SITES * 4) + threadIdx.x * 4, 0u);
+    // ---- every warp: the same padded segment layout, sites 2*lane and 2*lane+1 per lane
+    const unsigned c0 = (2 * lane < (unsigned)NS) ? lds32(cnt + (2 * lane) * 4) : 0u;
+    const unsigned c1 = (2 * lane + 1 < (unsigned)NS) ? lds32(cnt + (2 * lane + 1) * 4) : 0u;
+    const unsigned ch0 = (c0 + 31) >> 5, ch1 = (c1 + 31) >> 5;       // chunks of 32 pairs
+    unsigned incl = ch0 + ch1;
 #pragma unroll
-        for (int j = 0; j < EXPAND_SPT; ++j) {
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const unsigned start0 = incl - ch0 - ch1, start1 = start0 + ch0;  // first chunk of each site
+    const unsigned total_chunks = __shfl_sync(0xffffffffu, incl, 31);
+    // Scatter rounds.  The list holds LIST_CAP pairs; a round covers the chunks [r0, r_end) and a segment is
+    // never split across rounds (a segment has <= TILE/32 chunks, so every round makes progress).  One round
+    // is the rule; more are needed only when a tile enables more than LIST_CAP pairs in this group.
+    constexpr unsigned ROUND_CHUNKS = LIST_CAP / 32;
+    unsigned r0 = 0;
+#pragma unroll 1
+    do {
+      // end of this round: the start of the first segment that does not fit any more
+      unsigned r_end = total_chunks;
+      if (total_chunks > r0 + ROUND_CHUNKS) {
+        unsigned cand0 = (ch0 && start0 >= r0 && start0 + ch0 > r0 + ROUND_CHUNKS) ? start0 : 0xFFFFFFFFu;
+        unsigned cand1 = (ch1 && start1 >= r0 && start1 + ch1 > r0 + ROUND_CHUNKS) ? start1 : 0xFFFFFFFFu;
+        unsigned nxt = min(cand0, cand1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+        r_end = min(r_end, nxt);
+      }
+      if (r0) __syncthreads();                         // later rounds: the previous round's list is consumed
+      // ---- A2: scatter the pairs of the sites whose segment lies in this round
+#pragma unroll 1
+      for (int k = 0; k < NS; ++k) {
+        const unsigned st = __shfl_sync(0xffffffffu, (k & 1) ? start1 : start0, k >> 1);
+        const unsigned ck = __shfl_sync(0xffffffffu, (k & 1) ? c1 : c0, k >> 1);
+        if (ck == 0 || st < r0 || st + ((ck + 31) >> 5) > r_end) continue;
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
           const bool en = (masks[j] >> k) & 1;
           const unsigned m = __ballot_sync(0xffffffffu, en);
           if (m) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&c.item_cnt[k], (unsigned)__popc(m));
+            if (lane == 0) base = atoms_add(c.cur + k * 4, (unsigned)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (en) c.list[c.item_off[k] + base + __popc(m & ((1u << lane) - 1))] = ((unsigned)k << 16) | ((unsigned)j * EXPAND_BLOCK + threadIdx.x);
+            if (en) {
+              const unsigned pos = (st - r0) * 32 + base + __popc(m & ((1u << lane) - 1));
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(c.list + pos * 2), "h"((unsigned short)((unsigned)j * EXPAND_BLOCK + threadIdx.x)) : "memory");
+            }
           }
         }
       }
-      __syncthreads();
-      // ---- phase B: bodies, 32 list entries at a time (entries of one item are contiguous)
+      __syncthreads();                                 // list complete (also orders the clearing of the other totals buffer)
+      if (threadIdx.x < MAX_GROUP_SITES) sts32(c.cur + threadIdx.x * 4, 0u);   // cursors ready for the next scatter
+      // ---- B: bodies, one chunk (= 32 pairs of one site) per warp and step
 #pragma unroll 1
-      for (unsigned e0 = warp * 32; e0 < total; e0 += EXPAND_BLOCK) {
-        const unsigned e = e0 + lane;
-        if (e < total) {
-          const unsigned entry = c.list[e];
-          const unsigned loc = entry & 0xFFFFu;
-          const uint64_t i = c.tile_base + loc;
+      for (unsigned ch = r0 + warp; ch < r_end; ch += NWARPS) {
+        // site of this chunk: the last site whose first chunk is <= ch (an empty site shares its successor's start)
+        const int below = __popc(__ballot_sync(0xffffffffu, start0 <= ch && 2 * lane < (unsigned)NS)) +
+                          __popc(__ballot_sync(0xffffffffu, start1 <= ch && 2 * lane + 1 < (unsigned)NS));
+        const int k = below - 1;
+        const unsigned st = __shfl_sync(0xffffffffu, (k & 1) ? start1 : start0, k >> 1);
+        const unsigned ck = __shfl_sync(0xffffffffu, (k & 1) ? c1 : c0, k >> 1);
+        const unsigned e = (ch - st) * 32 + lane;      // index inside the site's segment
+        if (e < ck) {
+          unsigned short slot16;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(slot16) : "r"(c.list + ((st - r0) * 32 + e) * 2));
+          const unsigned slot = slot16;
           State s;
-          load_state(s, p.store + (c.first + i) * W);
-          CandSink<MULTI> sink{p, (c.first + i) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt, 0, 0};
-          ItemDispatch<BEGIN, END>::run((int)(entry >> 16) + BEGIN, s, sink);
-          if (sink.n) atomicAdd(&c.succ[loc], (unsigned)sink.n);
+#pragma unroll
+          for (int q = 0; q < W; ++q) s.w[q] = lds64(c.tile + (slot * W + q) * 8);
+          CandSink sink{(c.first + c.tile_base + slot) | ((uint64_t)p.rank << 40), c.wbuf, c.wcnt,
+                        p.count_actions ? p.ctr->action_counts : nullptr, 0, 0
+#ifdef KMC_ONE_PHASE
+                        , nullptr, nullptr, 0
+#endif
+          };
+          SiteDispatch<BEGIN, END>::run(k + BEGIN, s, sink);
           failed |= sink.failed;
         }
-        flush_stage<MULTI, false>(p, c.wbuf, c.wcnt, false, failed, xs);
+        flush_stage(p, c.wbuf, c.wcnt, false, failed);
       }
-    }
-    if (threadIdx.x < NI) c.item_cnt[threadIdx.x] = 0;
-    __syncthreads();                                   // list consumed before the next group refills it
-    GroupRunner2<G + 1, MULTI>::run(p, c, failed, xs);
+      r0 = r_end;
+    } while (r0 < total_chunks);
+    SiteGroupRunner<G + 1>::run(p, c, nsucc, failed);
   }
 };
-template <bool MULTI>
-struct GroupRunner2<M::NUM_GROUPS, MULTI> {
-  static __device__ __forceinline__ void run(const Params&, const TwoPhaseCtx&, int&, ExpandStats&) {}
+template <>
+struct SiteGroupRunner<M::NUM_SITE_GROUPS> {
+  static __device__ __forceinline__ void run(const Params&, const TileCtx&, unsigned (&)[SPT], int&) {}
 };
 
-template <bool MULTI>
-__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand2(Params p, uint64_t first, uint64_t count, int spt) {
-  extern __shared__ uint64_t stage[];   // [warps][STAGE_ROWS][ROW] | wcnt[warps] | list_count | list[LIST_CAP] | succ[TILE]
+__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t first, uint64_t count, unsigned tile_states) {
+  extern __shared__ __align__(16) uint64_t smem[];   // tile | stage | list | cnt[2][64] | cur[64] | wcnt[NWARPS]
   const int warp = threadIdx.x >> 5;
-  constexpr int NW = EXPAND_BLOCK / 32;
-  uint64_t* wbuf = stage + (size_t)warp * STAGE_ROWS * ROW;
-  unsigned* u = reinterpret_cast<unsigned*>(stage + (size_t)NW * STAGE_ROWS * ROW);
-  unsigned* wcnt = u + warp;
-  unsigned* list_count = u + NW;
-  unsigned* list = u + NW + 4;
-  unsigned* succ = list + LIST_CAP;
-  unsigned* item_cnt = succ + EXPAND_BLOCK * EXPAND_SPT;
-  unsigned* item_off = item_cnt + MAX_GROUP_ITEMS;
-  if (lane_id() == 0) *wcnt = 0;
-  if (threadIdx.x == 0) *list_count = 0;
-  if (threadIdx.x < MAX_GROUP_ITEMS) item_cnt[threadIdx.x] = 0;
-  __syncthreads();
+  TileCtx c;
+  c.tile = smem_addr(smem);
+  const uint32_t stage = c.tile + TILE * W * 8;
+  c.wbuf = stage + warp * (STAGE_ROWS * ROW * 8);
+  c.list = stage + STAGE_BYTES;
+  c.cnt = c.list + LIST_CAP * 2;
+  c.cur = c.cnt + 2 * MAX_GROUP_SITES * 4;
+  c.wcnt = c.cur + MAX_GROUP_SITES * 4 + warp * 4;
+  c.first = first;
+  if (lane_id() == 0) sts32(c.wcnt, 0u);
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
-  ExpandStats xs{0, 0};
-  const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
-  for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
-    for (int j = 0; j < spt; ++j) succ[j * EXPAND_BLOCK + threadIdx.x] = 0;
-    __syncthreads();                                   // succ[] zeroed before any body adds to it
-    TwoPhaseCtx c{first, tile_base, count, spt, wbuf, wcnt, list, list_count, succ, item_cnt, item_off};
-    GroupRunner2<0, MULTI>::run(p, c, failed, xs);
-    flush_stage<MULTI, false>(p, wbuf, wcnt, true, failed, xs);
-    __syncthreads();                                   // every body of this tile has added to succ[]
-#pragma unroll 1
-    for (int j = 0; j < spt; ++j) {
-      const unsigned loc = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
-      uint64_t i = tile_base + loc;
-      if (i >= count) continue;
-      const unsigned n = succ[loc];
-      gen += n;
-      if (n > maxfan) maxfan = n;
-      if (n == 0) {
-        ++dead;
-        if (p.check_deadlock) {
-          State s;
-          load_state(s, p.store + (first + i) * W);
-          record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+  // tile_states <= TILE: small levels use smaller tiles so that every SM still gets one
+  for (uint64_t tile_base = (uint64_t)blockIdx.x * tile_states; tile_base < count; tile_base += (uint64_t)gridDim.x * tile_states) {
+    c.tile_base = tile_base;
+    c.nvalid = (unsigned)min((uint64_t)tile_states, count - tile_base);
+    __syncthreads();                                   // every body of the previous tile has read its state
+    if (threadIdx.x < 3 * MAX_GROUP_SITES) sts32(c.cnt + threadIdx.x * 4, 0u);      // cnt[2][64] and cur[64]
+    {
+      // frontier tile -> shared memory, coalesced (128-bit loads when the rows are 16-byte aligned)
+      const uint64_t* src = p.store + (first + tile_base) * W;
+      const unsigned nwords = c.nvalid * W;
+      if (((W & 1) == 0)) {
+        const ulonglong2* src2 = reinterpret_cast<const ulonglong2*>(src);
+        for (unsigned i = threadIdx.x; i < nwords / 2; i += EXPAND_BLOCK) {
+          ulonglong2 v = __ldg(src2 + i);
+          asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(c.tile + i * 16), "l"(v.x), "l"(v.y) : "memory");
+        }
+      } else {
+        for (unsigned i = threadIdx.x; i < nwords; i += EXPAND_BLOCK) sts64(c.tile + i * 8, __ldg(src + i));
+      }
+    }
+    __syncthreads();
+    unsigned nsucc[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) nsucc[j] = 0;
+    SiteGroupRunner<0>::run(p, c, nsucc, failed);
+    flush_stage(p, c.wbuf, c.wcnt, true, failed);
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const unsigned slot = (unsigned)j * EXPAND_BLOCK + threadIdx.x;
+      if (slot < c.nvalid) {
+        gen += nsucc[j];
+        maxfan = max(maxfan, nsucc[j]);
+        if (nsucc[j] == 0) {
+          ++dead;
+          if (p.check_deadlock) {
+            State s;
+            load_state(s, p.store + (first + tile_base + slot) * W);
+            record_violation(p, s, p.parent[first + tile_base + slot], fingerprint(s), ~0ull);
+          }
         }
       }
     }
-    __syncthreads();                                   // succ[] is re-zeroed by the next tile
   }
+  // warp reduce the statistics, one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
     gen += __shfl_xor_sync(0xffffffffu, gen, o);
     dead += __shfl_xor_sync(0xffffffffu, dead, o);
@@ -713,31 +725,65 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand2(Params p, uint64_t 
   }
 }
 
-#ifndef EXPAND_MIN_BLOCKS
-#define EXPAND_MIN_BLOCKS 1
-#endif
+#ifdef KMC_ONE_PHASE
+// ----------------------------------------------------------------------------------------
+// K1, one-phase (round 1): comparison build only (-DKMC_ONE_PHASE, option "one_phase").  The
+// lowered Next is cut into NUM_GROUPS groups of ~1k instructions and the CTA sweeps ONE group at
+// a time over a tile of EXPAND_BLOCK x spt states (__syncthreads between groups keeps all warps
+// of the SM in the same group, so a fetched instruction line serves every warp).
+// ----------------------------------------------------------------------------------------
+static constexpr int EXPAND_SPT1 = 4;
+template <int G>
+struct GroupRunner {
+  static __device__ __forceinline__ void run(const Params& p, uint64_t first, uint64_t tile_base, uint64_t count,
+                                              int spt, unsigned (&nsucc)[EXPAND_SPT1], int& failed, uint32_t wbuf, uint32_t wcnt) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < EXPAND_SPT1; ++j) {
+      if (j < spt) {
+        uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
+        if (i < count) {
+          State s;
+          load_state(s, p.store + (first + i) * W);
+          CandSink sink{(first + i) | ((uint64_t)p.rank << 40), wbuf, wcnt, p.count_actions ? p.ctr->action_counts : nullptr, 0, 0,
+                        p.world == 1 ? p.cand : nullptr, &p.ctr->cand_count[0], p.region_rows};
+          M::expand_group(M::GroupTag<G>{}, s, sink);
+          nsucc[j] += (unsigned)sink.n;
+          failed |= sink.failed;
+        }
+        flush_stage(p, wbuf, wcnt, false, failed);
+      }
+    }
+    GroupRunner<G + 1>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
+  }
+};
+template <>
+struct GroupRunner<M::NUM_GROUPS> {
+  static __device__ __forceinline__ void run(const Params&, uint64_t, uint64_t, uint64_t, int, unsigned (&)[EXPAND_SPT1], int&,
+                                              uint32_t, uint32_t) {}
+};
 
-template <bool MULTI, bool FUSED>
-__global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_MIN_BLOCKS) k_expand(Params p, uint64_t first, uint64_t count, int spt) {
-  extern __shared__ uint64_t stage[];                       // [warps][STAGE_ROWS][ROW] then [warps] counters
+__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand1(Params p, uint64_t first, uint64_t count, int spt) {
+  extern __shared__ __align__(16) uint64_t smem[];          // [warps][STAGE_ROWS][ROW] then [warps] counters
   const int warp = threadIdx.x >> 5;
-  uint64_t* wbuf = stage + (size_t)warp * STAGE_ROWS * ROW;
-  unsigned* wcnt = reinterpret_cast<unsigned*>(stage + (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW) + warp;
-  if (lane_id() == 0) *wcnt = 0;
+  const uint32_t wbuf = smem_addr(smem) + warp * (STAGE_ROWS * ROW * 8);
+  const uint32_t wcnt = smem_addr(smem) + STAGE_BYTES + warp * 4;
+  if (lane_id() == 0) sts32(wcnt, 0u);
   __syncwarp();
   unsigned long long gen = 0, dead = 0;
   unsigned maxfan = 0;
   int failed = 0;
-  ExpandStats xs{0, 0};
   const uint64_t tile = (uint64_t)EXPAND_BLOCK * spt;
   for (uint64_t tile_base = (uint64_t)blockIdx.x * tile; tile_base < count; tile_base += (uint64_t)gridDim.x * tile) {
-    unsigned nsucc[EXPAND_SPT] = {};
-    GroupRunner<0, MULTI, FUSED>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt, xs);
-    flush_stage<MULTI, FUSED>(p, wbuf, wcnt, true, failed, xs);
-#pragma unroll 1
-    for (int j = 0; j < spt; ++j) {
+    unsigned nsucc[EXPAND_SPT1];
+#pragma unroll
+    for (int j = 0; j < EXPAND_SPT1; ++j) nsucc[j] = 0;
+    GroupRunner<0>::run(p, first, tile_base, count, spt, nsucc, failed, wbuf, wcnt);
+    flush_stage(p, wbuf, wcnt, true, failed);
+#pragma unroll
+    for (int j = 0; j < EXPAND_SPT1; ++j) {
       uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
-      if (i >= count) continue;
+      if (j >= spt || i >= count) continue;
       gen += nsucc[j];
       if (nsucc[j] > maxfan) maxfan = nsucc[j];
       if (nsucc[j] == 0) {
@@ -750,24 +796,20 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_MIN_BLOCKS) k_expand(Para
       }
     }
   }
-  // warp reduce the statistics, one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
     gen += __shfl_xor_sync(0xffffffffu, gen, o);
     dead += __shfl_xor_sync(0xffffffffu, dead, o);
     maxfan = max(maxfan, __shfl_xor_sync(0xffffffffu, maxfan, o));
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
-    xs.probes += __shfl_xor_sync(0xffffffffu, xs.probes, o);
-    xs.oom += __shfl_xor_sync(0xffffffffu, xs.oom, o);
   }
   if (lane_id() == 0) {
-    if (xs.probes) atomicAdd(&p.ctr->probes, (unsigned long long)xs.probes);
-    if (xs.oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)xs.oom);
     if (gen) atomicAdd(&p.ctr->generated, gen);
     if (dead) atomicAdd(&p.ctr->deadlocks, dead);
     if (maxfan) atomicMax(&p.ctr->max_fanout_seen, (unsigned long long)maxfan);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
   }
 }
+#endif  // KMC_ONE_PHASE
 
 __device__ __forceinline__ void load_row(State& s, uint64_t& meta, const uint64_t* rows, uint64_t i, bool valid) {
   meta = 0;
@@ -784,10 +826,16 @@ __device__ __forceinline__ void load_row(State& s, uint64_t& meta, const uint64_
 // occupancy than the added memory-level parallelism gains.)
 __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, const unsigned long long* n_ptr,
                                                  uint64_t n_fixed) {
-  const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
-  const uint64_t n_round = (n + 31) & ~31ull;
-  unsigned probes = 0, oom = 0;
+  uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
+  unsigned probes = 0, oom = 0, hits = 0;
   int failed = 0;
+  if (n_ptr && n > p.region_rows) {
+    // the expand kernel's slot claims ran past the region (it reports KMC_FAIL_CAND_FULL itself; the
+    // counter keeps counting): never read beyond the rows that were actually written
+    n = p.region_rows;
+    failed = KMC_FAIL_CAND_FULL;
+  }
+  const uint64_t n_round = (n + 31) & ~31ull;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
     const bool v0 = i < n;
@@ -795,16 +843,18 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
     uint64_t m0;
     load_row(s0, m0, rows, i, v0);
     Prefetched f0 = prefetch_row(p, s0, v0);
-    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
+    insert_row(p, s0, m0, v0, f0, probes, oom, hits, failed);
   }
   for (int o = 16; o > 0; o >>= 1) {
     probes += __shfl_xor_sync(0xffffffffu, probes, o);
     oom += __shfl_xor_sync(0xffffffffu, oom, o);
+    hits += __shfl_xor_sync(0xffffffffu, hits, o);
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
   }
   if (lane_id() == 0) {
     if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
     if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
+    if (hits) atomicAdd(&p.ctr->dcache_hits, (unsigned long long)hits);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
   }
 }
@@ -830,7 +880,7 @@ __global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
   }
   const uint64_t n = starts[MAX_WORLD];
   const uint64_t n_round = (n + 31) & ~31ull;
-  unsigned probes = 0, oom = 0;
+  unsigned probes = 0, oom = 0, hits = 0;
   int failed = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -847,16 +897,18 @@ __global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
       m0 = __ldcs(row + W);
     }
     Prefetched f0 = prefetch_row(p, s0, v0);
-    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
+    insert_row(p, s0, m0, v0, f0, probes, oom, hits, failed);
   }
   for (int o = 16; o > 0; o >>= 1) {
     probes += __shfl_xor_sync(0xffffffffu, probes, o);
     oom += __shfl_xor_sync(0xffffffffu, oom, o);
+    hits += __shfl_xor_sync(0xffffffffu, hits, o);
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
   }
   if (lane_id() == 0) {
     if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
     if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
+    if (hits) atomicAdd(&p.ctr->dcache_hits, (unsigned long long)hits);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
   }
 }
@@ -913,14 +965,12 @@ struct Engine {
   bool check_deadlock = M::CHECK_DEADLOCK;
   bool timing = true;
   bool count_actions = false;
-  bool fused = false;           // single-GPU kmc_run: insert from the expand kernel's staged flush (measured slower:
-                                // warps waiting on probe latency hold up the CTA-wide group barrier)
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
+  int dcache_log2 = 0;              // duplicate filter entries (log2), 0 = off
+  uint64_t* dcache = nullptr;
   uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
-  bool two_phase = false;           // K1 as guard phase + compacted body phase (k_expand2): correct, lanes/inst 12 -> 25,
-                                    // but 2.3x slower as built (per-item re-unpack in the guard phase, local-memory
-                                    // traffic of the non-inlined bodies); kept as an opt-in path, see profiles/README.md
+  bool one_phase = false;           // comparison only: the round-1 one-phase K1 (needs a -DKMC_ONE_PHASE build)
 
   uint64_t* table = nullptr;
   uint64_t table_slots = 0;
@@ -977,6 +1027,8 @@ struct Engine {
     p.world = world;
     p.check_deadlock = check_deadlock ? 1 : 0;
     p.count_actions = count_actions ? 1 : 0;
+    p.dcache = dcache;
+    p.dcache_shift = dcache ? (uint32_t)(64 - dcache_log2) : 0u;
     for (int r = 0; r < MAX_WORLD; ++r) p.peer_inbox[r] = peer_inbox[r];
     p.inbox_stride = inbox_stride;
     p.p2p = 0;
@@ -1066,13 +1118,6 @@ static int grid_for(const Engine& E, uint64_t n, int block, int per_sm) {
   return (int)g;
 }
 
-static size_t expand_smem_bytes() {
-  return (size_t)(EXPAND_BLOCK / 32) * STAGE_ROWS * ROW * 8 + (EXPAND_BLOCK / 32) * sizeof(unsigned);
-}
-static size_t expand2_smem_bytes() {
-  return expand_smem_bytes() + 16 + (size_t)LIST_CAP * 4 + (size_t)EXPAND_BLOCK * EXPAND_SPT * 4 + 2 * MAX_GROUP_ITEMS * 4;
-}
-
 static int engine_alloc(Engine& E) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1120,13 +1165,32 @@ static int engine_alloc(Engine& E) {
     CK(cudaMalloc(&E.inbox, 2 * E.inbox_stride * 8));
     CK(cudaMemset(E.inbox, 0, 2 * E.inbox_stride * 8));
   }
-  // the expand kernels stage successor rows in > 48 KB of dynamic shared memory
-  CK(cudaFuncSetAttribute(k_expand<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_expand<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_expand<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_bytes()));
-  if (E.two_phase) {
-    CK(cudaFuncSetAttribute(k_expand2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand2_smem_bytes()));
-    CK(cudaFuncSetAttribute(k_expand2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand2_smem_bytes()));
+  // the expand kernel keeps its state tile, the successor stage and the pair list in > 48 KB of dynamic shared memory
+  CK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPAND_SMEM_BYTES));
+#ifdef KMC_ONE_PHASE
+  CK(cudaFuncSetAttribute(k_expand1, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES + NWARPS * 4));
+#else
+  if (E.one_phase) {
+    E.last_error = "option one_phase needs a library built with -DKMC_ONE_PHASE";
+    return KMC_E_BADARG;
+  }
+#endif
+  if (E.dcache_log2) {
+    const size_t bytes = (size_t)8 << E.dcache_log2;
+    CK(cudaMalloc(&E.dcache, bytes));
+    // keep the filter resident in L2: persisting window on the engine's stream (the table probes stream past it)
+    size_t want = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+    if (want) {
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = E.dcache;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      av.accessPolicyWindow.hitRatio = (float)std::min<double>(1.0, (double)want / (double)bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      CK(cudaStreamSetAttribute(E.stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
   }
   CK(cudaMalloc(&E.ctr, sizeof(DevCounters)));
   CK(cudaMalloc(&E.viol_ring, (size_t)VIOL_RING * VIOL_ROW * 8));
@@ -1138,6 +1202,7 @@ static int engine_alloc(Engine& E) {
 static int engine_reset(Engine& E) {
   CK(cudaSetDevice(E.device));
   CK(cudaMemsetAsync(E.table, 0, E.table_slots * 8, E.stream));
+  if (E.dcache) CK(cudaMemsetAsync(E.dcache, 0, (size_t)8 << E.dcache_log2, E.stream));
   DevCounters h;
   memset(&h, 0, sizeof(h));
   CK(cudaMemcpyAsync(E.ctr, &h, sizeof(h), cudaMemcpyHostToDevice, E.stream));
@@ -1219,28 +1284,28 @@ static int launch_invariants(Engine& E, uint64_t first, uint64_t count_bound) {
   return KMC_OK;
 }
 
-static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool fused = false) {
+static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool p2p = false) {
   Params p = E.params();
-  // small levels: fewer states per thread so that every SM still gets a tile
-  int spt = EXPAND_SPT;
-  while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
-  uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
-  int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
-  const size_t smem = expand_smem_bytes();
-  grid *= EXPAND_MIN_BLOCKS;
-  if ((uint64_t)grid > tiles) grid = (int)std::max<uint64_t>(tiles, 1);
-  if (E.two_phase && !fused) {
-    const size_t smem2 = expand2_smem_bytes();
-    TimedLaunch t(E, 0);
-    if (E.world > 1) k_expand2<true><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);
-    else k_expand2<false><<<grid, EXPAND_BLOCK, smem2, E.stream>>>(p, first, count, spt);
+  p.p2p = p2p ? 1 : 0;
+  if (count == 0) return KMC_OK;
+  TimedLaunch t(E, 0);
+#ifdef KMC_ONE_PHASE
+  if (E.one_phase) {
+    int spt = EXPAND_SPT1;
+    while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
+    uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
+    int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
+    k_expand1<<<grid, EXPAND_BLOCK, STAGE_BYTES + NWARPS * 4, E.stream>>>(p, first, count, spt);
     CK(cudaGetLastError());
     return KMC_OK;
   }
-  TimedLaunch t(E, 0);
-  if (E.world > 1) k_expand<true, false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
-  else if (fused) k_expand<false, true><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
-  else k_expand<false, false><<<grid, EXPAND_BLOCK, smem, E.stream>>>(p, first, count, spt);
+#endif
+  // small levels: smaller tiles so that every SM still gets one (a tile is a multiple of 32 states)
+  uint64_t per_sm = (count + E.sms - 1) / E.sms;
+  unsigned tile_states = (unsigned)std::min<uint64_t>((uint64_t)TILE, std::max<uint64_t>(32, (per_sm + 31) & ~31ull));
+  uint64_t tiles = (count + tile_states - 1) / tile_states;
+  int grid = (int)std::min<uint64_t>(tiles, (uint64_t)E.sms);
+  k_expand<<<grid, EXPAND_BLOCK, EXPAND_SMEM_BYTES, E.stream>>>(p, first, count, tile_states);
   CK(cudaGetLastError());
   return KMC_OK;
 }
@@ -1333,19 +1398,11 @@ static int engine_run(Engine& E) {
   }
   while (!err && !stopped && level_end > level_first) {
     E.widths.push_back(level_end - level_first);
-    if (E.fused) {
-      // one launch per level: successors are inserted from the expand kernel's staged flush; only
-      // rows that overflowed a warp's stage (rare bursts) go through cand + k_insert
+    for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
+      uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
       if ((rc = reset_cand(E))) return rc;
-      if ((rc = launch_expand(E, level_first, level_end - level_first, true))) return rc;
-      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, 32 * 1024))) return rc;
-    } else {
-      for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
-        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
-        if ((rc = reset_cand(E))) return rc;
-        if ((rc = launch_expand(E, off, cnt))) return rc;
-        if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
-      }
+      if ((rc = launch_expand(E, off, cnt))) return rc;
+      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
     }
     if ((rc = launch_invariants(E, level_end, (level_end - level_first) * 2))) return rc;
     if ((rc = read_counters(E, &h))) return rc;
@@ -1389,6 +1446,7 @@ static int engine_run(Engine& E) {
     st.deadlocks = h.deadlocks;
     st.out_of_model = h.out_of_model;
     st.probes = h.probes;
+    st.dcache_hits = h.dcache_hits;
     st.levels = E.widths.size();
     st.gpu_ms_total = total_ms;
     st.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -1423,10 +1481,10 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "check_deadlock", &b)) E.check_deadlock = b;
   if (json_bool(options_json, "timing", &b)) E.timing = b;
   if (json_bool(options_json, "count_actions", &b)) E.count_actions = b;
-  if (json_bool(options_json, "fused", &b)) E.fused = b;
   if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
   if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
-  if (json_bool(options_json, "two_phase", &b)) E.two_phase = b;
+  if (json_num(options_json, "dcache_log2", &d)) E.dcache_log2 = (int)d;
+  if (json_bool(options_json, "one_phase", &b)) E.one_phase = b;
   if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
     // a cudaStream_t handle of the calling process (e.g. torch.cuda.current_stream().cuda_stream): engine
@@ -1451,6 +1509,7 @@ void kmcm_destroy(kmcm_ctx* c) {
   cudaFree(E.store);
   cudaFree(E.parent);
   cudaFree(E.cand);
+  cudaFree(E.dcache);
   cudaFree(E.recv);
   if (E.peers_open)
     for (uint32_t r = 0; r < E.world; ++r)
@@ -1507,22 +1566,6 @@ int kmcm_action_counts(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) 
   *n = std::min<size_t>(M::NUM_ACTIONS, E.action_counts.size());
   for (size_t i = 0; i < *n && i < cap; ++i) out[i] = E.action_counts[i];
   return KMC_OK;
-}
-
-// Diagnostic, not part of include/kspecmc.h: per-group SM cycles of K1 (all zero unless built with
-// -DKMC_GROUP_CLOCKS).  *n = number of groups.
-int kmcm_group_clocks(const kmcm_ctx* c, uint64_t* out, size_t cap, size_t* n) {
-  if (!c || !n) return KMC_E_BADARG;
-  *n = (size_t)M::NUM_GROUPS;
-#ifdef KMC_GROUP_CLOCKS
-  unsigned long long h[M::NUM_GROUPS + 1];
-  if (cudaMemcpyFromSymbol(h, g_group_clocks, sizeof(h)) != cudaSuccess) return KMC_E_CUDA;
-  for (size_t i = 0; i < *n && i < cap; ++i) out[i] = h[i];
-  return KMC_OK;
-#else
-  for (size_t i = 0; i < *n && i < cap; ++i) out[i] = 0;
-  return KMC_E_STATE;
-#endif
 }
 
 int kmcm_violation(const kmcm_ctx* c, kmc_violation_t* out) {
@@ -1703,6 +1746,7 @@ int kmcm_shard_level_done(kmcm_ctx* c, uint64_t* level_first, uint64_t* level_co
     E.stats.deadlocks = h.deadlocks;
     E.stats.out_of_model = h.out_of_model;
     E.stats.probes = h.probes;
+    E.stats.dcache_hits = h.dcache_hits;
     E.stats.table_slots = E.table_slots;
     E.stats.max_states = E.max_states;
     if (E.level_count) E.widths.push_back(E.level_count);
@@ -1748,16 +1792,9 @@ int kmcm_shard_expand_p2p(kmcm_ctx* c, uint64_t first, uint64_t count) {
   if (count > E.chunk_states) return KMC_E_BADARG;
   int rc = reset_cand(E);
   if (rc) return rc;
+  if ((rc = launch_expand(E, first, count, true))) return rc;
   Params p = E.params();
   p.p2p = 1;
-  if (count) {
-    int spt = EXPAND_SPT;
-    while (spt > 1 && count < (uint64_t)E.sms * EXPAND_BLOCK * spt) spt >>= 1;
-    uint64_t tiles = (count + (uint64_t)EXPAND_BLOCK * spt - 1) / ((uint64_t)EXPAND_BLOCK * spt);
-    int grid = (int)std::min<uint64_t>(std::max<uint64_t>(tiles, 1), (uint64_t)E.sms);
-    TimedLaunch t(E, 0);
-    k_expand<true, false><<<grid, EXPAND_BLOCK, expand_smem_bytes(), E.stream>>>(p, first, count, spt);
-  }
   {
     TimedLaunch t(E, 2);
     k_publish_counts<<<1, 32, 0, E.stream>>>(p);

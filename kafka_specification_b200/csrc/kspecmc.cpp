@@ -96,7 +96,8 @@ int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out) {
 void kmc_destroy(kmc_ctx* c) {
   if (!c) return;
   if (c->inner && c->destroy) c->destroy(c->inner);
-  if (c->dl) dlclose(c->dl);
+  // the model library stays mapped until the process exits: a process usually re-creates contexts of the
+  // same model, and a loaded-library audit of the process (/proc/self/maps) then shows which lowered model ran
   delete c;
 }
 

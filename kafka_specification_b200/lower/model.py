@@ -309,44 +309,79 @@ def _split_unit(lines: list[str], max_blocks: int) -> list[list[str]]:
     return [[l[2:] if l.startswith("  ") else l for l in _render(temps + c, 1)] for c in chunks if c]
 
 
-def _unit_items(lines: list[str], max_prefix_temps: int = 3):
-    """Splits one unit into items.  An item = (guard temps, guard conditions, body lines): the
-    guard is the chain of leading `if`s that are preceded by at most a few temporaries -- cheap to
-    evaluate for every state; the body (which re-checks the chain) is the whole top-level block and
-    is executed only for the (state, item) pairs whose guard held, compacted across the CTA."""
+def _is_core(n: _Node) -> bool:
+    """A core is the bare block emit_successor() opens: it packs and emits exactly one successor (or
+    reports a layout trap) and contains no further branching on the state."""
+    if not n.is_block or n.cond is not None or n.text != "{":
+        return False
+    for k in n.children:
+        if not k.is_block and (k.text.startswith("State n = s;") or k.text.startswith("sink.fail(")):
+            return True
+        if k.is_block and any((not c.is_block) and c.text.startswith("State n = s;") for c in k.children):
+            return True
+    return False
+
+
+def _unit_sites(lines: list[str]):
+    """Splits one unit into emit sites.  Returns (guard_tree, sites):
+
+    * ``guard_tree`` is the unit's own code with every core replaced by a marker node ``@site k`` (k = index
+      of the site inside the unit); rendered by ``_render_guard`` it evaluates, for one state, the COMPLETE
+      path condition of every site (all the `if`s between the unit root and the core), sharing the common
+      prefixes exactly as expand() does;
+    * ``sites[k]`` = body lines of site k: the (pure, hence safely speculated) temporaries of the blocks on
+      its path, flattened, followed by the core.  The body does not re-check the path condition: it is run
+      only for (state, site) pairs whose mask bit is set.
+    """
     nodes = _prune(_parse_unit(lines))
-    items = []
-    root_temps: list[_Node] = []
-    i = 0
-    while i < len(nodes):
-        n = nodes[i]
-        if not n.is_block:
-            root_temps.append(n)
-            i += 1
-            continue
-        group = [n]
-        while i + 1 < len(nodes) and not nodes[i + 1].is_block and nodes[i + 1].text.startswith("else "):
-            group.append(nodes[i + 1])
-            i += 1
-        conds, temps = [], []
-        cur = n
-        while True:
-            if cur.cond is not None:
-                conds.append(cur.cond)
-            kids = cur.children
-            lead = [k for k in kids if not k.is_block and k.text.startswith("const ")]
-            blocks = [k for k in kids if k.is_block]
-            others = [k for k in kids if not k.is_block and not k.text.startswith("const ")]
-            if len(blocks) == 1 and not others and len(lead) <= max_prefix_temps and kids[-1] is blocks[0] \
-                    and (blocks[0].cond is not None or not lead):
-                temps.extend(lead)
-                cur = blocks[0]
+    sites: list[list[str]] = []
+
+    def walk(ns: list[_Node], path_temps: list[_Node]) -> list[_Node]:
+        out: list[_Node] = []
+        temps_here: list[_Node] = []
+        for n in ns:
+            if not n.is_block:
+                if not n.text.startswith("const "):
+                    raise LowerError(f"internal: statement outside a core: {n.text}")
+                temps_here.append(n)
+                out.append(n)
                 continue
-            break
-        items.append({"root_temps": _render(list(root_temps), 1), "guard_temps": _render(temps, 1),
-                      "conds": conds, "body": _render(group, 1)})
-        i += 1
-    return items
+            if _is_core(n):
+                out.append(_Node(f"@site {len(sites)}"))
+                sites.append(_render(path_temps + temps_here, 1) + _render([n], 1))
+                continue
+            blk = _Node(n.text, n.cond, True)
+            blk.children = walk(n.children, path_temps + temps_here)
+            out.append(blk)
+        return out
+
+    return walk(nodes, []), sites
+
+
+def _render_guard(tree: list[_Node], lo: int, hi: int, bit0: int) -> list[str]:
+    """Guard code of the sites lo <= k < hi of one unit: site k sets mask bit (bit0 + k - lo).  Blocks without a
+    site in the window are dropped; temporaries stay (the C++ compiler removes the unused ones)."""
+    def prune(ns):
+        out, live = [], False
+        for n in ns:
+            if n.is_block:
+                sub, sub_live = prune(n.children)
+                if sub_live:
+                    blk = _Node(n.text, n.cond, True)
+                    blk.children = sub
+                    out.append(blk)
+                    live = True
+            elif n.text.startswith("@site "):
+                k = int(n.text[6:])
+                if lo <= k < hi:
+                    out.append(_Node(f"m |= 1ull << {bit0 + k - lo};"))
+                    live = True
+            else:
+                out.append(n)
+        return out, live
+
+    nodes, live = prune(tree)
+    return _render(nodes, 1) if live else []
 
 
 # ---------------------------------------------------------------------------
@@ -466,7 +501,7 @@ struct State {{ uint64_t w[W]; }};
 
 
 def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | None = None,
-                group_lines: int = 160) -> LoweredModel:
+                group_lines: int = 160, max_group_sites: int = 64, guard_lines: int = 400) -> LoweredModel:
     cfg = parse_cfg(cfg_text)
     root = load_root(module, search_dirs)
     lw = Lowerer(root, cfg)
@@ -518,32 +553,48 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     lw.gen_next(start, {}, None)
     lw.end_unit()
     expand_prologue = list(lw.prologue)
-    # pack consecutive units into groups of bounded size: each group becomes one function that the
-    # CUDA engine sweeps over a tile of states, so that its code stays resident in the SM's
-    # instruction cache (a fully unrolled Next is hundreds of KB of SASS)
+    # One-phase form: pack consecutive units into groups of bounded size: each group becomes one function that
+    # is swept over a tile of states, so that its code stays resident in the SM's instruction cache (a fully
+    # unrolled Next is hundreds of KB of SASS).  Kept for the host-side harness / CPU baseline and as the
+    # engine's -DKMC_ONE_PHASE comparison build.
     groups: list[list[str]] = []
-    group_units: list[list[list[str]]] = []
     cur_lines: list[str] = []
-    cur_units: list[list[str]] = []
-    cur_items = 0
     all_units: list[list[str]] = []
     for lines, _ in lw.units:
-        all_units.extend(_split_unit(lines, 40) if len(_unit_items(lines)) > 40 else [lines])
+        top_blocks = sum(1 for n in _prune(_parse_unit(lines)) if n.is_block)
+        all_units.extend(_split_unit(lines, 40) if top_blocks > 40 else [lines])
     for lines in all_units:
-        n_it = len(_unit_items(lines))
-        if cur_lines and (len(cur_lines) + len(lines) > group_lines or cur_items + n_it > 48):
+        if cur_lines and len(cur_lines) + len(lines) > group_lines:
             groups.append(cur_lines)
-            group_units.append(cur_units)
-            cur_lines, cur_units, cur_items = [], [], 0
+            cur_lines = []
         cur_lines = cur_lines + ["  {"] + ["  " + l for l in lines] + ["  }"]
-        cur_units.append(lines)
-        cur_items += n_it
     if cur_lines or not groups:
         groups.append(cur_lines)
-        group_units.append(cur_units)
     expand_lines = [l for g in groups for l in g]
-    # guard/body items per group (consumed by the CUDA engine's two-phase expand kernel)
-    group_items = [[it for u in units for it in _unit_items(u)] for units in group_units]
+    # Two-phase form (what the CUDA expand kernel runs): every emit site becomes an item = (complete path
+    # condition, straight-line body).  A site group = a run of consecutive sites (<= 64: one mask word; bounded
+    # guard code so that the guard phase of a group stays in the instruction cache); a unit with more sites than
+    # fit is covered by several windows of the same guard tree.
+    unit_trees = [_unit_sites(lines) for lines in all_units]
+    site_bodies: list[list[str]] = []
+    site_groups: list[dict] = []            # {"begin": first site, "count": n, "guard": lines}
+    cur = {"begin": 0, "count": 0, "guard": []}
+    for tree, sites in unit_trees:
+        k = 0
+        while k < len(sites):
+            room = max_group_sites - cur["count"]
+            if room == 0 or (cur["count"] and len(cur["guard"]) > guard_lines):
+                site_groups.append(cur)
+                cur = {"begin": cur["begin"] + cur["count"], "count": 0, "guard": []}
+                continue
+            n = min(room, len(sites) - k)
+            g = _render_guard(tree, k, k + n, cur["count"])
+            cur["guard"] += ["  {"] + ["  " + l for l in g] + ["  }"]
+            cur["count"] += n
+            k += n
+        site_bodies.extend(sites)
+    if cur["count"] or not site_groups:
+        site_groups.append(cur)
     max_fanout = lw.emit_sites
 
     # invariants
@@ -593,6 +644,8 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
         sym_lines = list(lw.prologue) + list(lw.cg.lines)
 
     name = name or module
+    if len(lw.actions) > 255:
+        raise LowerError(f"{len(lw.actions)} sub-actions: the parent word holds the action id in 8 bits (<= 255)")
     body_digest = hashlib.sha256(("\n".join(expand_lines + inv_lines + con_lines + sym_lines) + cfg_text).encode()).hexdigest()[:16]
     unpack = lw.unpack_lines()
 
@@ -606,8 +659,13 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
         parts.append("  {" + ", ".join(f"0x{w:x}ull" for w in wds) + "},")
     parts.append("};")
     parts.append("/* successor enumeration: sink.emit(const State&, int action) per successor; sink.fail(code) on a layout trap.")
-    parts.append("   expand() = the groups in order; a group is a slice of the Next disjuncts/bindings small enough to stay")
-    parts.append("   in the instruction cache while the engine sweeps it over a tile of states. */")
+    parts.append("   Two equivalent forms (tests prove they enumerate the same multiset):")
+    parts.append("   one-phase   expand() = expand_group<0..NUM_GROUPS-1> in order; a group is a slice of the Next disjuncts /")
+    parts.append("               bindings small enough to stay in the instruction cache while it is swept over a tile of states;")
+    parts.append("   two-phase   site_mask(SiteGroupTag<g>, s) = bit k set iff the COMPLETE path condition of emit site")
+    parts.append("               SITE_GROUP_BEGIN[g] + k holds for s;  site_body(SiteTag<i>, s, sink) = the straight-line")
+    parts.append("               successor construction of site i, run only for (state, site) pairs whose bit is set. */")
+    parts.append("#ifndef KMC_NO_ONE_PHASE")
     parts.append(f"static constexpr int NUM_GROUPS = {len(groups)};")
     parts.append("template <int G> struct GroupTag {};")
     for gi, glines in enumerate(groups):
@@ -620,61 +678,48 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     for gi in range(len(groups)):
         parts.append(f"  expand_group(GroupTag<{gi}>{{}}, s, sink);")
     parts.append("}")
-    # two-phase form of the same code: item_guard = cheap leading guards, item_body = the full block
-    parts.append("/* Two-phase form: an item is one top-level guarded block of a unit.  item_guard(I, s) evaluates only the")
-    parts.append("   cheap leading guards; item_body(I, s, sink) is the complete block (it re-checks them).  For every state,")
-    parts.append("   running item_body for exactly the items whose guard holds emits the same successors as expand(). */")
-    parts.append("template <int I> struct ItemTag {};")
-    n_items = 0
-    begins = []
-    for gi, items in enumerate(group_items):
-        begins.append(n_items)
-        for it in items:
-            parts.append(f"KMC_HD bool item_guard(ItemTag<{n_items}>, const State& s) {{")
-            parts.extend(unpack)
-            parts.extend(expand_prologue)
-            parts.extend(it["root_temps"])
-            parts.extend(it["guard_temps"])
-            parts.append("  return " + (" && ".join(f"({c})" for c in it["conds"]) if it["conds"] else "true") + ";")
-            parts.append("}")
-            parts.append(f"template <class Sink> KMC_HD void item_body(ItemTag<{n_items}>, const State& s, Sink& sink) {{")
-            parts.extend(unpack)
-            parts.extend(expand_prologue)
-            parts.extend(it["root_temps"])
-            parts.extend(it["body"])
-            parts.append("}")
-            n_items += 1
-    begins.append(n_items)
-    # one guard function per group: a single unpack, bit k = item (GROUP_ITEM_BEGIN[g] + k) is enabled
-    for gi, items in enumerate(group_items):
-        if len(items) > 64:
-            raise LowerError(f"group {gi} has {len(items)} items (> 64); lower group_lines")
-        parts.append(f"KMC_HD uint64_t group_guard_mask(GroupTag<{gi}>, const State& s) {{")
+    parts.append("#endif  // KMC_NO_ONE_PHASE")
+    n_sites = len(site_bodies)
+    parts.append(f"static constexpr int NUM_SITES = {n_sites};")
+    parts.append(f"static constexpr int NUM_SITE_GROUPS = {len(site_groups)};")
+    parts.append("static constexpr int SITE_GROUP_BEGIN[NUM_SITE_GROUPS + 1] = {" +
+                 ", ".join(str(g["begin"]) for g in site_groups) + f", {n_sites}" + "};")
+    parts.append("template <int G> struct SiteGroupTag {};")
+    parts.append("template <int I> struct SiteTag {};")
+    for gi, g in enumerate(site_groups):
+        parts.append(f"KMC_HD uint64_t site_mask(SiteGroupTag<{gi}>, const State& s) {{")
         parts.extend(unpack)
         parts.extend(expand_prologue)
         parts.append("  uint64_t m = 0;")
-        for k, it in enumerate(items):
-            parts.append("  {")
-            parts.extend(it["root_temps"])
-            parts.extend(it["guard_temps"])
-            cond = " && ".join(f"({c})" for c in it["conds"]) if it["conds"] else "true"
-            parts.append(f"    if ({cond}) m |= 1ull << {k};")
-            parts.append("  }")
+        parts.extend(g["guard"])
         parts.append("  return m;")
         parts.append("}")
-    parts.append(f"static constexpr int NUM_ITEMS = {n_items};")
-    parts.append("static constexpr int GROUP_ITEM_BEGIN[NUM_GROUPS + 1] = {" + ", ".join(str(b) for b in begins) + "};")
-    parts.append("/* expand() through the two-phase form (used by tests to prove both forms agree) */")
-    parts.append("template <int I, int END> struct ItemLoop {")
-    parts.append("  template <class Sink> static KMC_HD void run(const State& s, Sink& sink) {")
-    parts.append("    if (item_guard(ItemTag<I>{}, s)) item_body(ItemTag<I>{}, s, sink);")
-    parts.append("    ItemLoop<I + 1, END>::run(s, sink);")
+    for i, body in enumerate(site_bodies):
+        parts.append(f"template <class Sink> KMC_HD void site_body(SiteTag<{i}>, const State& s, Sink& sink) {{")
+        parts.extend(unpack)
+        parts.extend(expand_prologue)
+        parts.extend(body)
+        parts.append("}")
+    parts.append("/* expand() through the two-phase form (host-side tests prove both forms agree) */")
+    parts.append("template <int I, int END> struct SiteLoop {")
+    parts.append("  template <class Sink> static KMC_HD void run(uint64_t m, int bit, const State& s, Sink& sink) {")
+    parts.append("    if ((m >> bit) & 1) site_body(SiteTag<I>{}, s, sink);")
+    parts.append("    SiteLoop<I + 1, END>::run(m, bit + 1, s, sink);")
     parts.append("  }")
     parts.append("};")
-    parts.append("template <int END> struct ItemLoop<END, END> {")
+    parts.append("template <int END> struct SiteLoop<END, END> {")
+    parts.append("  template <class Sink> static KMC_HD void run(uint64_t, int, const State&, Sink&) {}")
+    parts.append("};")
+    parts.append("template <int G> struct SiteGroupLoop {")
+    parts.append("  template <class Sink> static KMC_HD void run(const State& s, Sink& sink) {")
+    parts.append("    SiteLoop<SITE_GROUP_BEGIN[G], SITE_GROUP_BEGIN[G + 1]>::run(site_mask(SiteGroupTag<G>{}, s), 0, s, sink);")
+    parts.append("    SiteGroupLoop<G + 1>::run(s, sink);")
+    parts.append("  }")
+    parts.append("};")
+    parts.append("template <> struct SiteGroupLoop<NUM_SITE_GROUPS> {")
     parts.append("  template <class Sink> static KMC_HD void run(const State&, Sink&) {}")
     parts.append("};")
-    parts.append("template <class Sink> KMC_HD void expand_items(const State& s, Sink& sink) { ItemLoop<0, NUM_ITEMS>::run(s, sink); }")
+    parts.append("template <class Sink> KMC_HD void expand_sites(const State& s, Sink& sink) { SiteGroupLoop<0>::run(s, sink); }")
     parts.append("/* index of the first violated INVARIANT of the cfg, or -1 */")
     parts.append("KMC_HD int first_violated_invariant(const State& s) {")
     parts.extend(unpack)

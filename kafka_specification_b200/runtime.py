@@ -40,7 +40,7 @@ class Stats(ctypes.Structure):
         ("gpu_ms_total", ctypes.c_double), ("gpu_ms_expand", ctypes.c_double), ("gpu_ms_insert", ctypes.c_double),
         ("launches_expand", ctypes.c_uint64), ("launches_insert", ctypes.c_uint64), ("launches_other", ctypes.c_uint64),
         ("wall_ms", ctypes.c_double), ("table_slots", ctypes.c_uint64), ("max_states", ctypes.c_uint64),
-        ("complete", ctypes.c_uint64), ("gpu_ms_invariant", ctypes.c_double),
+        ("complete", ctypes.c_uint64), ("gpu_ms_invariant", ctypes.c_double), ("dcache_hits", ctypes.c_uint64),
     ]
 
     def as_dict(self) -> dict:
