@@ -73,11 +73,11 @@ typedef struct {
   uint64_t launches_insert;
   uint64_t launches_other;
   double wall_ms;           /* host wall clock of the last kmc_run                        */
-  uint64_t table_slots;     /* fingerprint-set capacity in 8-byte slots                   */
+  uint64_t table_slots;     /* fingerprint-set capacity in slots (slot_bytes each)        */
   uint64_t max_states;      /* state-store capacity                                       */
   uint64_t complete;        /* 1 if the search ran to an empty queue                      */
   double gpu_ms_invariant;  /* sum over invariant-kernel launches (counted in launches_other) */
-  uint64_t dcache_hits;     /* candidates the L2-resident duplicate filter answered (no DRAM probe) */
+  uint64_t slot_bytes;      /* 8: 64-bit fingerprints (one-word states); 16: 128-bit keys (the state itself when it fits) */
 } kmc_stats_t;
 
 typedef struct {
@@ -96,7 +96,7 @@ typedef struct {
   int32_t num_init;
   int32_t max_fanout;       /* static bound on successors per state                       */
   int32_t check_deadlock;
-  int32_t exact;            /* 1: fingerprint is a bijection of the state (<= 64 bits)    */
+  int32_t exact;            /* 1: the set key is a bijection of the state (<= 63 bits, or two words stored as a 128-bit key) */
   char name[128];
   char digest[32];
 } kmc_model_info_t;
@@ -108,7 +108,6 @@ typedef struct {
  * "stop_after_states":N (bounded run: stop at the first level end holding >= N states),
  * "stream":H (cudaStream_t handle of the caller to launch on instead of a private stream),
  * "fanout_bound":K (successors per state assumed when sizing frontier chunks; default min(MAX_FANOUT, 32)),
- * "dcache_log2":L (L2-resident duplicate filter of 2^L recently confirmed fingerprints in front of the set; 0 = off),
  * "one_phase":false (comparison only: the round-1 one-phase expand kernel; needs a -DKMC_ONE_PHASE library).  */
 int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out);
 void kmc_destroy(kmc_ctx* ctx);

@@ -80,6 +80,8 @@ def model_dir(name: str) -> str:
 VARIANTS = {
     "": ["-DKMC_NO_ONE_PHASE"],
     "1p": ["-DKMC_ONE_PHASE"],
+    "b512": ["-DKMC_NO_ONE_PHASE", "-DEXPAND_BLOCK_THREADS=512", "-DEXPAND_CTAS_PER_SM=2"],    # two 512-thread CTAs per SM
+    "bs4": ["-DKMC_NO_ONE_PHASE", "-DKMC_BUCKET_SLOTS=4"],                                   # 64-byte buckets of 16-byte keys
 }
 
 
@@ -95,12 +97,15 @@ def _engine_stamp() -> str:
     return h.hexdigest()[:16]
 
 
-def lower_to_dir(module: str, cfg_path: str, name: str):
+def lower_to_dir(module: str, cfg_path: str, name: str, **lower_kw):
     """Lower and write model.h / model.json; returns the LoweredModel."""
+    import time
     from .lower.model import lower_model
     with open(cfg_path) as f:
         cfg_text = f.read()
-    m = lower_model(module, tla_search_dirs(), cfg_text, name=name)
+    t0 = time.time()
+    m = lower_model(module, tla_search_dirs(), cfg_text, name=name, **lower_kw)
+    lower_seconds = time.time() - t0
     d = model_dir(name)
     os.makedirs(d, exist_ok=True)
     hdr = os.path.join(d, "model.h")
@@ -110,6 +115,7 @@ def lower_to_dir(module: str, cfg_path: str, name: str):
             f.write(m.header)
     meta = m.meta()
     meta["cfg"] = os.path.relpath(cfg_path, ROOT)
+    meta["lower_seconds"] = round(lower_seconds, 2)      # parse + lower on the build host (part of a cold start)
     with open(os.path.join(d, "model.json"), "w") as f:
         json.dump(meta, f, indent=1)
     return m

@@ -72,9 +72,27 @@ __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
   return x;
 }
 
-// States of <= 63 bits get a *bijective* fingerprint (the set is then exact, not
-// probabilistic); wider states get a chained 64-bit mix (TLC's FP64 contract: collisions
-// possible with probability ~ n^2 / 2^65).  0 is reserved for "empty slot".
+// Identity of a state in the set.
+//   one-word models (<= 63 bits): the fingerprint is a bijection of the state, stored in 8-byte slots   -> exact
+//   two-word models             : the key IS the packed state (16-byte slots, 128-bit CAS)              -> exact
+//                                 (all-ones marks an empty slot; the lowering proves no valid state packs to it)
+//   wider models                : a 128-bit fingerprint (two independent 64-bit chains) in 16-byte slots;
+//                                 collision probability ~ n^2 / 2^129 (TLC's FP64 contract squared)
+// The 64-bit fingerprint also picks the bucket and the owner rank and orders counterexamples.
+static constexpr bool KEY128 = (W >= 2);
+static constexpr bool EXACT_SET = EXACT64 || (W == 2 && !M::ALL_ONES_POSSIBLE);
+#ifndef KMC_BUCKET_SLOTS
+#define KMC_BUCKET_SLOTS 2            // 16-byte slots per bucket: 2 = one 32 B sector, 4 = one 64 B DRAM burst
+#endif
+static constexpr int BUCKET_SLOTS = KEY128 ? KMC_BUCKET_SLOTS : 4;
+static constexpr int SLOT_BYTES = KEY128 ? 16 : 8;
+
+struct alignas(16) Key128 {
+  unsigned long long lo, hi;
+};
+__host__ __device__ __forceinline__ bool key_eq(const Key128& a, const Key128& b) { return a.lo == b.lo && a.hi == b.hi; }
+__host__ __device__ __forceinline__ bool key_empty(const Key128& a) { return (a.lo & a.hi) == ~0ull; }
+
 __host__ __device__ __forceinline__ uint64_t fingerprint(const State& s) {
   if (EXACT64) return fmix64(s.w[0] + 1);
   uint64_t h = fmix64(s.w[0] + 0x9E3779B97F4A7C15ull);
@@ -82,21 +100,55 @@ __host__ __device__ __forceinline__ uint64_t fingerprint(const State& s) {
   for (int i = 1; i < W; ++i) h = fmix64(h ^ (s.w[i] + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)));
   return h ? h : 1;
 }
+__host__ __device__ __forceinline__ uint64_t fmix64b(uint64_t x) {     // a second, unrelated finaliser (splitmix64's)
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ __forceinline__ Key128 key_of(const State& s, uint64_t fp) {
+  Key128 k;
+  if (W == 2 && !M::ALL_ONES_POSSIBLE) {
+    k.lo = s.w[0];
+    k.hi = s.w[W - 1];
+  } else {
+    uint64_t h = fmix64b(s.w[0] ^ 0xD6E8FEB86659FD93ull);
+#pragma unroll
+    for (int i = 1; i < W; ++i) h = fmix64b((h << 7 | h >> 57) ^ s.w[i]);
+    k.lo = fp;
+    k.hi = h;
+    if (key_empty(k)) k.hi ^= 1;
+  }
+  return k;
+}
 
-// Identity of a state in the set (and its owner rank): with SYMMETRY it is the fingerprint of the
-// orbit representative (smallest packed image under the symmetry group, TLC's symmetry reduction);
-// the state that is stored, expanded and shown in traces stays the one that was actually reached.
-// canonicalize() is a few thousand instructions (n!-1 permuted images); kept out of line so that it exists once
-// per kernel instead of once per call site (nvcc time of a symmetric model: 16 min -> 2 min).
-__host__ __device__ __noinline__ uint64_t canonical_fp(const State& s) {
+// With SYMMETRY the identity is that of the orbit representative (smallest packed image under the symmetry
+// group, TLC's symmetry reduction); the state that is stored, expanded and shown in traces stays the one that
+// was actually reached.  canonicalize() is a few thousand instructions (n!-1 permuted images); kept out of
+// line so that it exists once per kernel instead of once per call site (nvcc time of a symmetric model: 16 min -> 2 min).
+struct Ident {
+  uint64_t fp;
+  Key128 key;
+};
+__host__ __device__ __noinline__ void canonical_ident(const State& s, Ident& id) {
   State c;
   M::canonicalize(s, c);
-  return fingerprint(c);
+  id.fp = fingerprint(c);
+  id.key = key_of(c, id.fp);
 }
-__host__ __device__ __forceinline__ uint64_t state_fp(const State& s) {
-  if (M::HAS_SYMMETRY) return canonical_fp(s);
-  return fingerprint(s);
+__host__ __device__ __forceinline__ Ident state_ident(const State& s) {
+  Ident id;
+  if (M::HAS_SYMMETRY) {
+    canonical_ident(s, id);
+  } else {
+    id.fp = fingerprint(s);
+    id.key = key_of(s, id.fp);
+  }
+  return id;
 }
+__host__ __device__ __forceinline__ uint64_t state_fp(const State& s) { return state_ident(s).fp; }
 
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t fp, uint32_t world) {
   return (uint32_t)(((fp >> 32) * (uint64_t)world) >> 32);
@@ -115,7 +167,6 @@ struct DevCounters {
   unsigned long long fail;
   unsigned long long max_fanout_seen;
   unsigned long long viol_count;         // rows claimed in the violator ring
-  unsigned long long dcache_hits;        // candidates recognised as duplicates by the L2-resident filter
   unsigned long long action_counts[64];
 };
 
@@ -127,7 +178,7 @@ static constexpr int VIOL_RING = 1024;
 static constexpr int VIOL_ROW = W + 3;
 
 struct Params {
-  uint64_t* table;
+  void* table;              // 8-byte slots (one-word models) or 16-byte slots
   uint64_t bucket_mask;     // #buckets - 1
   uint64_t* store;
   uint64_t* parent;
@@ -139,11 +190,6 @@ struct Params {
   uint32_t rank, world;
   uint32_t check_deadlock;
   uint32_t count_actions;
-  // duplicate filter in front of the set: a direct-mapped array of recently confirmed fingerprints, small enough
-  // to stay in L2 (pinned there with an access-policy window).  A hit proves the fingerprint is in the set (an
-  // entry is only written after the set held it), so the duplicate costs no DRAM probe; a miss costs one L2 read.
-  uint64_t* dcache;
-  uint32_t dcache_shift;    // 64 - log2(entries); 0 = filter off
   // fused exchange (world > 1, after kmc_shard_open_peers): every rank's inbox, mapped into this
   // process through CUDA IPC.  An inbox is two buffers (double buffering); a buffer is an 8-word
   // header (rows sent by each source rank) followed by world regions of region_rows rows.
@@ -178,7 +224,7 @@ __device__ __noinline__ void record_violation(const Params& p, const State& s, u
 // ----------------------------------------------------------------------------------------
 // K2 primitives: the fingerprint set
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ ulonglong2 ld_bucket_half(const uint64_t* p) {
+__device__ __forceinline__ ulonglong2 ld_cg128(const void* p) {
   // L2-coherent 128-bit load, no L1 allocation: buckets are touched once per probe
   ulonglong2 v;
   asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
@@ -187,27 +233,59 @@ __device__ __forceinline__ ulonglong2 ld_bucket_half(const uint64_t* p) {
 
 __device__ __forceinline__ uint64_t bucket_of(uint64_t fp, uint64_t bucket_mask) { return (fp ^ (fp >> 31)) & bucket_mask; }
 
-// returns 1 = inserted (new), 0 = already present, -1 = table full.  (lo, hi) = the first bucket,
-// loaded by the caller ahead of time so that several probes are in flight per thread.
-__device__ __forceinline__ int fpset_insert_pre(uint64_t* table, uint64_t bucket_mask, uint64_t fp, ulonglong2 lo,
-                                                 ulonglong2 hi, unsigned& probes) {
-  uint64_t b = bucket_of(fp, bucket_mask);
-  for (int attempt = 0; attempt < 512; ++attempt) {
-    uint64_t* base = table + (b << 2);
-    if (attempt) {
-      lo = ld_bucket_half(base);
-      hi = ld_bucket_half(base + 2);
-    }
-    ++probes;
-    uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
-    if (v[0] == fp || v[1] == fp || v[2] == fp || v[3] == fp) return 0;
+// One bucket = BUCKET_SLOTS slots, loaded with 128-bit loads: 8-byte slots -> 2 loads of 2 slots each (32 B);
+// 16-byte slots -> one load per slot.
+static constexpr int BUCKET_LOADS = KEY128 ? BUCKET_SLOTS : 2;
+struct Bucket {
+  ulonglong2 v[BUCKET_LOADS];
+};
+__device__ __forceinline__ const char* bucket_addr(const void* table, uint64_t b) {
+  return static_cast<const char*>(table) + b * (uint64_t)(BUCKET_SLOTS * SLOT_BYTES);
+}
+__device__ __forceinline__ Bucket ld_bucket(const void* table, uint64_t b) {
+  Bucket k;
+  const char* base = bucket_addr(table, b);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (v[k] == 0) {
-        unsigned long long old = atomicCAS((unsigned long long*)(base + k), 0ull, (unsigned long long)fp);
-        if (old == 0) return 1;
-        if (old == fp) return 0;
-        // another fingerprint took the slot: keep scanning (slots never empty again)
+  for (int i = 0; i < BUCKET_LOADS; ++i) k.v[i] = ld_cg128(base + 16 * i);
+  return k;
+}
+
+// returns 1 = inserted (new), 0 = already present, -1 = table full.  `bk` = the first bucket, loaded by the
+// caller ahead of time.  Correctness of the lock-free insert: slots never return to empty and every inserter
+// of a key scans the same probe sequence without skipping an unverified slot, so a key occupies at most one
+// slot; a stale read is harmless (the CAS decides).
+__device__ __forceinline__ int set_insert_pre(void* table, uint64_t bucket_mask, const Ident& id, Bucket bk, unsigned& probes) {
+  uint64_t b = bucket_of(id.fp, bucket_mask);
+  for (int attempt = 0; attempt < 512; ++attempt) {
+    if (attempt) bk = ld_bucket(table, b);
+    ++probes;
+    if constexpr (KEY128) {
+      Key128* base = reinterpret_cast<Key128*>(const_cast<char*>(bucket_addr(table, b)));
+#pragma unroll
+      for (int k = 0; k < BUCKET_SLOTS; ++k)
+        if (bk.v[k].x == id.key.lo && bk.v[k].y == id.key.hi) return 0;
+#pragma unroll
+      for (int k = 0; k < BUCKET_SLOTS; ++k) {
+        if ((bk.v[k].x & bk.v[k].y) == ~0ull) {
+          const Key128 empty{~0ull, ~0ull};
+          Key128 old = atomicCAS(base + k, empty, id.key);          // ATOMG.E.CAS.128
+          if (key_empty(old)) return 1;
+          if (key_eq(old, id.key)) return 0;
+          // another key took the slot: keep scanning (slots never empty again)
+        }
+      }
+    } else {
+      uint64_t* base = reinterpret_cast<uint64_t*>(const_cast<char*>(bucket_addr(table, b)));
+      const uint64_t fp = id.fp;
+      uint64_t v[4] = {bk.v[0].x, bk.v[0].y, bk.v[1].x, bk.v[1].y};
+      if (v[0] == fp || v[1] == fp || v[2] == fp || v[3] == fp) return 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (v[k] == 0) {
+          unsigned long long old = atomicCAS((unsigned long long*)(base + k), 0ull, (unsigned long long)fp);
+          if (old == 0) return 1;
+          if (old == fp) return 0;
+        }
       }
     }
     b = (b + 1) & bucket_mask;
@@ -215,85 +293,72 @@ __device__ __forceinline__ int fpset_insert_pre(uint64_t* table, uint64_t bucket
   return -1;
 }
 
-__device__ __forceinline__ int fpset_insert(uint64_t* table, uint64_t bucket_mask, uint64_t fp, unsigned& probes) {
-  const uint64_t* base = table + (bucket_of(fp, bucket_mask) << 2);
-  ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
-  return fpset_insert_pre(table, bucket_mask, fp, lo, hi, probes);
+__device__ __forceinline__ int set_insert(void* table, uint64_t bucket_mask, const Ident& id, unsigned& probes) {
+  return set_insert_pre(table, bucket_mask, id, ld_bucket(table, bucket_of(id.fp, bucket_mask)), probes);
 }
 
-__device__ __forceinline__ int fpset_contains(const uint64_t* table, uint64_t bucket_mask, uint64_t fp) {
-  uint64_t b = bucket_of(fp, bucket_mask);
+__device__ __forceinline__ int set_contains(const void* table, uint64_t bucket_mask, const Ident& id) {
+  uint64_t b = bucket_of(id.fp, bucket_mask);
   for (int attempt = 0; attempt < 512; ++attempt) {
-    const uint64_t* base = table + (b << 2);
-    ulonglong2 lo = ld_bucket_half(base), hi = ld_bucket_half(base + 2);
-    if (lo.x == fp || lo.y == fp || hi.x == fp || hi.y == fp) return 1;
-    if (lo.x == 0 || lo.y == 0 || hi.x == 0 || hi.y == 0) return 0;
+    Bucket bk = ld_bucket(table, b);
+    bool any_empty = false;
+    if constexpr (KEY128) {
+#pragma unroll
+      for (int k = 0; k < BUCKET_SLOTS; ++k) {
+        if (bk.v[k].x == id.key.lo && bk.v[k].y == id.key.hi) return 1;
+        any_empty |= (bk.v[k].x & bk.v[k].y) == ~0ull;
+      }
+    } else {
+      const uint64_t fp = id.fp;
+      if (bk.v[0].x == fp || bk.v[0].y == fp || bk.v[1].x == fp || bk.v[1].y == fp) return 1;
+      any_empty = bk.v[0].x == 0 || bk.v[0].y == 0 || bk.v[1].x == 0 || bk.v[1].y == 0;
+    }
+    if (any_empty) return 0;
     b = (b + 1) & bucket_mask;
   }
   return 0;
 }
 
 // Warp-collective insert of one candidate row per lane (invalid lanes pass valid = false):
-// constraint check, fingerprint, bucket probe + CAS, ballot/popc compaction of the winners into the
-// state store, parent link.  Used by k_insert (rows from HBM) and by the fused flush of k_expand
-// (rows from the warp's shared-memory stage).
+// constraint check, identity, bucket probe + CAS, ballot/popc compaction of the winners into the
+// state store, parent link.
 struct Prefetched {
-  uint64_t fp;
-  ulonglong2 lo, hi;
+  Ident id;
+  Bucket bk;
   bool inmodel;
-  bool cached;      // duplicate filter hit: the fingerprint is known to be in the set
 };
 
-__device__ __forceinline__ uint64_t dcache_slot(uint64_t fp, uint32_t shift) { return (fp * 0x9E3779B97F4A7C15ull) >> shift; }
-
-// first half of an insert: fingerprint + issue the bucket loads (no dependent use yet)
+// first half of an insert: identity + issue the bucket loads (no dependent use yet)
 __device__ __forceinline__ Prefetched prefetch_row(const Params& p, const State& s, bool valid) {
   Prefetched f;
-  f.fp = 0;
-  f.lo = f.hi = make_ulonglong2(0, 0);
+  f.id.fp = 0;
+  f.id.key = Key128{0, 0};
+#pragma unroll
+  for (int i = 0; i < BUCKET_LOADS; ++i) f.bk.v[i] = make_ulonglong2(0, 0);
   f.inmodel = false;
-  f.cached = false;
   if (valid) {
     f.inmodel = (M::NUM_CONSTRAINTS == 0) || M::in_model(s);
-    f.fp = state_fp(s);
-    if (f.inmodel) {
-      if (p.dcache_shift) {
-        uint64_t c;
-        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(c) : "l"(p.dcache + dcache_slot(f.fp, p.dcache_shift)));
-        f.cached = (c == f.fp);
-      }
-      if (!f.cached) {
-        const uint64_t* base = p.table + (bucket_of(f.fp, p.bucket_mask) << 2);
-        f.lo = ld_bucket_half(base);
-        f.hi = ld_bucket_half(base + 2);
-      }
-    }
+    f.id = state_ident(s);
+    if (f.inmodel) f.bk = ld_bucket(p.table, bucket_of(f.id.fp, p.bucket_mask));
   }
   return f;
 }
 
 __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint64_t meta, bool valid, const Prefetched& f,
-                                            unsigned& probes, unsigned& oom, unsigned& hits, int& failed) {
+                                            unsigned& probes, unsigned& oom, int& failed) {
   bool is_new = false;
   if (valid) {
-    const bool inmodel = f.inmodel;
-    const uint64_t fp = f.fp;
-    if (inmodel) {
-      if (f.cached) {
-        ++hits;
-      } else {
-        int r = fpset_insert_pre(p.table, p.bucket_mask, fp, f.lo, f.hi, probes);
-        if (r < 0) failed = KMC_FAIL_TABLE_FULL;
-        is_new = r > 0;
-        if (p.dcache_shift && r >= 0) p.dcache[dcache_slot(fp, p.dcache_shift)] = fp;
-      }
+    if (f.inmodel) {
+      int r = set_insert_pre(p.table, p.bucket_mask, f.id, f.bk, probes);
+      if (r < 0) failed = KMC_FAIL_TABLE_FULL;
+      is_new = r > 0;
     } else {
       ++oom;
       // TLC also checks invariants on successors discarded by a CONSTRAINT; they are not stored,
       // so that (rare) case is handled here.  New in-model states are checked by k_invariants (K3).
       if (M::NUM_INVARIANTS > 0) {
         int inv = M::first_violated_invariant(s);
-        if (inv >= 0) record_violation(p, s, meta, fp, (uint64_t)inv);
+        if (inv >= 0) record_violation(p, s, meta, f.id.fp, (uint64_t)inv);
       }
     }
   }
@@ -328,6 +393,9 @@ __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint
 // st.shared / atom.shared so that no generic-address store (ST + QSPC) is ever generated.
 #ifndef EXPAND_BLOCK_THREADS
 #define EXPAND_BLOCK_THREADS 1024
+#endif
+#ifndef EXPAND_CTAS_PER_SM
+#define EXPAND_CTAS_PER_SM 1          // 2 (with 512 threads): one CTA's barrier waits are covered by the other CTA
 #endif
 static constexpr int EXPAND_BLOCK = EXPAND_BLOCK_THREADS;
 static constexpr int NWARPS = EXPAND_BLOCK / 32;
@@ -484,8 +552,8 @@ __device__ __forceinline__ void load_state(State& s, const uint64_t* src) {
 // Successor counts per state (deadlock detection, "states generated") are popc(mask).
 // ----------------------------------------------------------------------------------------
 static constexpr int STAGE_BYTES = NWARPS * STAGE_ROWS * ROW * 8;
-static constexpr int FIXED_SMEM_BYTES = STAGE_BYTES + LIST_CAP * 2 + (3 * MAX_GROUP_SITES + NWARPS + 8) * 4;
-static constexpr int SPT_FIT = (227 * 1024 - 1024 - FIXED_SMEM_BYTES) / (EXPAND_BLOCK * W * 8);
+static constexpr int FIXED_SMEM_BYTES = STAGE_BYTES + LIST_CAP * 2 + (4 * MAX_GROUP_SITES + NWARPS + 8) * 4;
+static constexpr int SPT_FIT = (227 * 1024 / EXPAND_CTAS_PER_SM - 1024 - FIXED_SMEM_BYTES) / (EXPAND_BLOCK * W * 8);
 static constexpr int SPT = SPT_FIT > 4 ? 4 : SPT_FIT;
 static_assert(SPT >= 1, "state too wide for the expand kernel's shared-memory tile");
 static constexpr int TILE = EXPAND_BLOCK * SPT;
@@ -497,6 +565,7 @@ struct TileCtx {
   uint32_t list;        // [LIST_CAP] u16 tile slots, per-site segments
   uint32_t cnt;         // [2][MAX_GROUP_SITES] enabled pairs per site (double-buffered across groups)
   uint32_t cur;         // [MAX_GROUP_SITES] scatter cursors
+  uint32_t seg;         // [MAX_GROUP_SITES] first chunk of each site's segment
   uint32_t wbuf, wcnt;
   uint64_t first, tile_base;
   unsigned nvalid;      // states in this tile
@@ -536,7 +605,9 @@ struct SiteGroupRunner {
     const unsigned lane = lane_id();
     const unsigned warp = threadIdx.x >> 5;
     const uint32_t cnt = c.cnt + (G & 1) * (MAX_GROUP_SITES * 4);
-    // ---- A1: masks of this thread's states, per-site totals
+    // ---- A1: masks of this thread's states; every enabled (state, site) pair bumps the site's total.
+    // (One shared-memory atomic per pair: ~3 per state.  A ballot/popc census over all sites and states cost
+    // 60 % of the kernel's instructions in the first version of this kernel, profiles/README.md r2a.)
     uint64_t masks[SPT];
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
@@ -550,12 +621,14 @@ struct SiteGroupRunner {
         nsucc[j] += (unsigned)__popcll(masks[j]);
       }
     }
-#pragma unroll 1
-    for (int k = 0; k < NS; ++k) {
-      unsigned n = 0;
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) n += __popc(__ballot_sync(0xffffffffu, (masks[j] >> k) & 1));
-      if (lane == 0 && n) atoms_add(cnt + k * 4, n);
+    for (int j = 0; j < SPT; ++j) {
+      uint64_t m = masks[j];
+      while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        atoms_add(cnt + k * 4, 1u);
+      }
     }
     __syncthreads();                                   // totals complete; B of the previous group finished
     // the other totals buffer (read last by B of group G-1) is cleared for A1 of group G+1
@@ -572,9 +645,13 @@ struct SiteGroupRunner {
     }
     const unsigned start0 = incl - ch0 - ch1, start1 = start0 + ch0;  // first chunk of each site
     const unsigned total_chunks = __shfl_sync(0xffffffffu, incl, 31);
-    // Scatter rounds.  The list holds LIST_CAP pairs; a round covers the chunks [r0, r_end) and a segment is
-    // never split across rounds (a segment has <= TILE/32 chunks, so every round makes progress).  One round
-    // is the rule; more are needed only when a tile enables more than LIST_CAP pairs in this group.
+    // segment starts where every thread of the CTA can look them up by site (all warps store the same values)
+    sts32(c.seg + (2 * lane) * 4, start0);
+    sts32(c.seg + (2 * lane + 1) * 4, start1);
+    __syncwarp();
+    // Scatter rounds.  The list holds LIST_CAP pairs; a round covers the chunks [r0, r_end) = the sites [k_lo, k_hi),
+    // and a segment is never split across rounds (a segment has <= TILE/32 chunks, so every round makes
+    // progress).  One round is the rule; more are needed only when a tile enables more than LIST_CAP pairs here.
     constexpr unsigned ROUND_CHUNKS = LIST_CAP / 32;
     unsigned r0 = 0;
 #pragma unroll 1
@@ -589,26 +666,24 @@ struct SiteGroupRunner {
         for (int o = 16; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
         r_end = min(r_end, nxt);
       }
+      // sites of this round = those whose (non-empty) segment starts in [r0, r_end): a contiguous index range
+      const unsigned in0 = __ballot_sync(0xffffffffu, ch0 && start0 >= r0 && start0 < r_end);
+      const unsigned in1 = __ballot_sync(0xffffffffu, ch1 && start1 >= r0 && start1 < r_end);
+      int k_lo = 64, k_hi = 0;
+      if (in0) { k_lo = min(k_lo, 2 * (__ffs(in0) - 1)); k_hi = max(k_hi, 2 * (31 - __clz(in0)) + 1); }
+      if (in1) { k_lo = min(k_lo, 2 * (__ffs(in1) - 1) + 1); k_hi = max(k_hi, 2 * (31 - __clz(in1)) + 2); }
       if (r0) __syncthreads();                         // later rounds: the previous round's list is consumed
-      // ---- A2: scatter the pairs of the sites whose segment lies in this round
-#pragma unroll 1
-      for (int k = 0; k < NS; ++k) {
-        const unsigned st = __shfl_sync(0xffffffffu, (k & 1) ? start1 : start0, k >> 1);
-        const unsigned ck = __shfl_sync(0xffffffffu, (k & 1) ? c1 : c0, k >> 1);
-        if (ck == 0 || st < r0 || st + ((ck + 31) >> 5) > r_end) continue;
+      // ---- A2: every thread scatters its own pairs: slot = cursor[site]++ inside the site's segment
 #pragma unroll
-        for (int j = 0; j < SPT; ++j) {
-          const bool en = (masks[j] >> k) & 1;
-          const unsigned m = __ballot_sync(0xffffffffu, en);
-          if (m) {
-            unsigned base = 0;
-            if (lane == 0) base = atoms_add(c.cur + k * 4, (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (en) {
-              const unsigned pos = (st - r0) * 32 + base + __popc(m & ((1u << lane) - 1));
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(c.list + pos * 2), "h"((unsigned short)((unsigned)j * EXPAND_BLOCK + threadIdx.x)) : "memory");
-            }
-          }
+      for (int j = 0; j < SPT; ++j) {
+        uint64_t m = masks[j];
+        while (m) {
+          const int k = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          if (k < k_lo || k >= k_hi) continue;         // empty sites in between have no pairs
+          const unsigned st = lds32(c.seg + k * 4);
+          const unsigned pos = (st - r0) * 32 + atoms_add(c.cur + k * 4, 1u);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(c.list + pos * 2), "h"((unsigned short)((unsigned)j * EXPAND_BLOCK + threadIdx.x)) : "memory");
         }
       }
       __syncthreads();                                 // list complete (also orders the clearing of the other totals buffer)
@@ -651,8 +726,8 @@ struct SiteGroupRunner<M::NUM_SITE_GROUPS> {
   static __device__ __forceinline__ void run(const Params&, const TileCtx&, unsigned (&)[SPT], int&) {}
 };
 
-__global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t first, uint64_t count, unsigned tile_states) {
-  extern __shared__ __align__(16) uint64_t smem[];   // tile | stage | list | cnt[2][64] | cur[64] | wcnt[NWARPS]
+__global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_CTAS_PER_SM) k_expand(Params p, uint64_t first, uint64_t count, unsigned tile_states) {
+  extern __shared__ __align__(16) uint64_t smem[];   // tile | stage | list | cnt[2][64] | cur[64] | seg[64] | wcnt[NWARPS]
   const int warp = threadIdx.x >> 5;
   TileCtx c;
   c.tile = smem_addr(smem);
@@ -661,7 +736,8 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand(Params p, uint64_t f
   c.list = stage + STAGE_BYTES;
   c.cnt = c.list + LIST_CAP * 2;
   c.cur = c.cnt + 2 * MAX_GROUP_SITES * 4;
-  c.wcnt = c.cur + MAX_GROUP_SITES * 4 + warp * 4;
+  c.seg = c.cur + MAX_GROUP_SITES * 4;
+  c.wcnt = c.seg + MAX_GROUP_SITES * 4 + warp * 4;
   c.first = first;
   if (lane_id() == 0) sts32(c.wcnt, 0u);
   unsigned long long gen = 0, dead = 0;
@@ -827,7 +903,7 @@ __device__ __forceinline__ void load_row(State& s, uint64_t& meta, const uint64_
 __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, const unsigned long long* n_ptr,
                                                  uint64_t n_fixed) {
   uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_fixed;
-  unsigned probes = 0, oom = 0, hits = 0;
+  unsigned probes = 0, oom = 0;
   int failed = 0;
   if (n_ptr && n > p.region_rows) {
     // the expand kernel's slot claims ran past the region (it reports KMC_FAIL_CAND_FULL itself; the
@@ -843,18 +919,16 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
     uint64_t m0;
     load_row(s0, m0, rows, i, v0);
     Prefetched f0 = prefetch_row(p, s0, v0);
-    insert_row(p, s0, m0, v0, f0, probes, oom, hits, failed);
+    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
   }
   for (int o = 16; o > 0; o >>= 1) {
     probes += __shfl_xor_sync(0xffffffffu, probes, o);
     oom += __shfl_xor_sync(0xffffffffu, oom, o);
-    hits += __shfl_xor_sync(0xffffffffu, hits, o);
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
   }
   if (lane_id() == 0) {
     if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
     if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
-    if (hits) atomicAdd(&p.ctr->dcache_hits, (unsigned long long)hits);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
   }
 }
@@ -880,7 +954,7 @@ __global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
   }
   const uint64_t n = starts[MAX_WORLD];
   const uint64_t n_round = (n + 31) & ~31ull;
-  unsigned probes = 0, oom = 0, hits = 0;
+  unsigned probes = 0, oom = 0;
   int failed = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -897,18 +971,16 @@ __global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
       m0 = __ldcs(row + W);
     }
     Prefetched f0 = prefetch_row(p, s0, v0);
-    insert_row(p, s0, m0, v0, f0, probes, oom, hits, failed);
+    insert_row(p, s0, m0, v0, f0, probes, oom, failed);
   }
   for (int o = 16; o > 0; o >>= 1) {
     probes += __shfl_xor_sync(0xffffffffu, probes, o);
     oom += __shfl_xor_sync(0xffffffffu, oom, o);
-    hits += __shfl_xor_sync(0xffffffffu, hits, o);
     failed = max(failed, __shfl_xor_sync(0xffffffffu, failed, o));
   }
   if (lane_id() == 0) {
     if (probes) atomicAdd(&p.ctr->probes, (unsigned long long)probes);
     if (oom) atomicAdd(&p.ctr->out_of_model, (unsigned long long)oom);
-    if (hits) atomicAdd(&p.ctr->dcache_hits, (unsigned long long)hits);
     if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
   }
 }
@@ -929,19 +1001,23 @@ __global__ void __launch_bounds__(256) k_invariants(Params p, uint64_t first, co
   }
 }
 
-__global__ void k_fpset_put(uint64_t* table, uint64_t bucket_mask, const uint64_t* fps, uint64_t n, uint8_t* seen,
+// The set alone (FPSet.put / contains): the caller's 64-bit fingerprints are the identities; with 16-byte
+// slots the key is the fingerprint and its second mix.
+__global__ void k_fpset_put(void* table, uint64_t bucket_mask, const uint64_t* fps, uint64_t n, uint8_t* seen,
                             DevCounters* ctr, int insert) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint64_t fp = fps[i] ? fps[i] : 1;
+    Ident id;
+    id.fp = fps[i] ? fps[i] : 1;
+    id.key = Key128{id.fp, fmix64b(id.fp)};
     if (insert) {
       unsigned probes = 0;
-      int r = fpset_insert(table, bucket_mask, fp, probes);
+      int r = set_insert(table, bucket_mask, id, probes);
       if (r < 0) atomicCAS(&ctr->fail, 0ull, (unsigned long long)KMC_FAIL_TABLE_FULL);
       if (r > 0) atomicAdd(&ctr->store_tail, 1ull);
       seen[i] = r == 0;
     } else {
-      seen[i] = (uint8_t)fpset_contains(table, bucket_mask, fp);
+      seen[i] = (uint8_t)set_contains(table, bucket_mask, id);
     }
   }
 }
@@ -967,13 +1043,11 @@ struct Engine {
   bool count_actions = false;
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
-  int dcache_log2 = 0;              // duplicate filter entries (log2), 0 = off
-  uint64_t* dcache = nullptr;
   uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
   bool one_phase = false;           // comparison only: the round-1 one-phase K1 (needs a -DKMC_ONE_PHASE build)
 
-  uint64_t* table = nullptr;
-  uint64_t table_slots = 0;
+  void* table = nullptr;
+  uint64_t table_slots = 0;             // slots of SLOT_BYTES each
   uint64_t* store = nullptr;
   uint64_t* parent = nullptr;
   uint64_t* cand = nullptr;
@@ -1015,7 +1089,7 @@ struct Engine {
   Params params() const {
     Params p;
     p.table = table;
-    p.bucket_mask = (table_slots >> 2) - 1;
+    p.bucket_mask = table_slots / BUCKET_SLOTS - 1;
     p.store = store;
     p.parent = parent;
     p.max_states = max_states;
@@ -1027,8 +1101,6 @@ struct Engine {
     p.world = world;
     p.check_deadlock = check_deadlock ? 1 : 0;
     p.count_actions = count_actions ? 1 : 0;
-    p.dcache = dcache;
-    p.dcache_shift = dcache ? (uint32_t)(64 - dcache_log2) : 0u;
     for (int r = 0; r < MAX_WORLD; ++r) p.peer_inbox[r] = peer_inbox[r];
     p.inbox_stride = inbox_stride;
     p.p2p = 0;
@@ -1135,15 +1207,28 @@ static int engine_alloc(Engine& E) {
   if (E.l2_fetch) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)E.l2_fetch));
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  if (E.table_log2 == 0) {
-    // default: a quarter of free memory for the set, rounded down to a power of two, <= 2^31 slots
-    int lg = 20;
-    while (lg < 31 && ((size_t)8 << (lg + 1)) <= free_b / 4) ++lg;
+  // Default sizing from the memory that is actually free: candidate buffers first, then set + store + parent
+  // links share the rest (2.5 slots per state: load <= 0.4, rounded to a power of two).
+  if (E.cand_bytes == 0) E.cand_bytes = std::min<uint64_t>(free_b / 8, (E.world > 1 ? 24ull : 12ull) << 30);
+  const uint64_t cand_total = E.cand_bytes * (E.world > 1 ? 4 : 1);          // + recv + two inbox buffers
+  const uint64_t budget = free_b > cand_total + (512ull << 20) ? (uint64_t)((free_b - cand_total) * 0.94) : 0;
+  const uint64_t per_state = (uint64_t)W * 8 + 8;
+  if (E.table_log2 == 0 && E.max_states == 0) {
+    int lg = 34;
+    while (lg > 16 && ((uint64_t)SLOT_BYTES << lg) + (uint64_t)((1ull << lg) / 2.5) * per_state > budget) --lg;
+    E.table_log2 = lg;
+    E.max_states = (uint64_t)((1ull << lg) / 2.5);
+  } else if (E.table_log2 == 0) {
+    int lg = 16;
+    while (lg < 34 && (1ull << lg) < (uint64_t)(2.5 * (double)E.max_states)) ++lg;
     E.table_log2 = lg;
   }
   E.table_slots = 1ull << E.table_log2;
-  if (E.max_states == 0) E.max_states = E.table_slots / 2;
-  if (E.cand_bytes == 0) E.cand_bytes = std::min<uint64_t>(free_b / 6, (E.world > 1 ? 24ull : 12ull) << 30);
+  if (E.max_states == 0) {
+    const uint64_t table_bytes = E.table_slots * SLOT_BYTES;
+    const uint64_t room = budget > table_bytes ? (budget - table_bytes) / per_state : 0;
+    E.max_states = std::max<uint64_t>(1024, std::min<uint64_t>(E.table_slots / 2, room));
+  }
   uint64_t rows_total = E.cand_bytes / (ROW * 8);
   E.region_rows = rows_total / E.world;
   if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
@@ -1154,7 +1239,7 @@ static int engine_alloc(Engine& E) {
   if (E.fanout_bound == 0) E.fanout_bound = std::min<uint32_t>((uint32_t)M::MAX_FANOUT, 32u);
   E.chunk_states = std::max<uint64_t>(1, E.region_rows / E.fanout_bound);
   if (E.own_stream) CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&E.table, E.table_slots * 8));
+  CK(cudaMalloc(&E.table, E.table_slots * SLOT_BYTES));
   CK(cudaMalloc(&E.store, E.max_states * W * 8));
   CK(cudaMalloc(&E.parent, E.max_states * 8));
   CK(cudaMalloc(&E.cand, E.region_rows * E.world * ROW * 8));
@@ -1175,23 +1260,6 @@ static int engine_alloc(Engine& E) {
     return KMC_E_BADARG;
   }
 #endif
-  if (E.dcache_log2) {
-    const size_t bytes = (size_t)8 << E.dcache_log2;
-    CK(cudaMalloc(&E.dcache, bytes));
-    // keep the filter resident in L2: persisting window on the engine's stream (the table probes stream past it)
-    size_t want = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
-    if (want) {
-      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-      cudaStreamAttrValue av;
-      memset(&av, 0, sizeof(av));
-      av.accessPolicyWindow.base_ptr = E.dcache;
-      av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-      av.accessPolicyWindow.hitRatio = (float)std::min<double>(1.0, (double)want / (double)bytes);
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      CK(cudaStreamSetAttribute(E.stream, cudaStreamAttributeAccessPolicyWindow, &av));
-    }
-  }
   CK(cudaMalloc(&E.ctr, sizeof(DevCounters)));
   CK(cudaMalloc(&E.viol_ring, (size_t)VIOL_RING * VIOL_ROW * 8));
   CK(cudaEventCreate(&E.ev_begin));
@@ -1201,8 +1269,7 @@ static int engine_alloc(Engine& E) {
 
 static int engine_reset(Engine& E) {
   CK(cudaSetDevice(E.device));
-  CK(cudaMemsetAsync(E.table, 0, E.table_slots * 8, E.stream));
-  if (E.dcache) CK(cudaMemsetAsync(E.dcache, 0, (size_t)8 << E.dcache_log2, E.stream));
+  CK(cudaMemsetAsync(E.table, KEY128 ? 0xFF : 0, E.table_slots * SLOT_BYTES, E.stream));      // empty marker: all-ones keys / zero fingerprints
   DevCounters h;
   memset(&h, 0, sizeof(h));
   CK(cudaMemcpyAsync(E.ctr, &h, sizeof(h), cudaMemcpyHostToDevice, E.stream));
@@ -1301,10 +1368,11 @@ static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool p2p = f
   }
 #endif
   // small levels: smaller tiles so that every SM still gets one (a tile is a multiple of 32 states)
-  uint64_t per_sm = (count + E.sms - 1) / E.sms;
-  unsigned tile_states = (unsigned)std::min<uint64_t>((uint64_t)TILE, std::max<uint64_t>(32, (per_sm + 31) & ~31ull));
+  const uint64_t ctas = (uint64_t)E.sms * EXPAND_CTAS_PER_SM;
+  uint64_t per_cta = (count + ctas - 1) / ctas;
+  unsigned tile_states = (unsigned)std::min<uint64_t>((uint64_t)TILE, std::max<uint64_t>(32, (per_cta + 31) & ~31ull));
   uint64_t tiles = (count + tile_states - 1) / tile_states;
-  int grid = (int)std::min<uint64_t>(tiles, (uint64_t)E.sms);
+  int grid = (int)std::min<uint64_t>(tiles, ctas);
   k_expand<<<grid, EXPAND_BLOCK, EXPAND_SMEM_BYTES, E.stream>>>(p, first, count, tile_states);
   CK(cudaGetLastError());
   return KMC_OK;
@@ -1446,11 +1514,11 @@ static int engine_run(Engine& E) {
     st.deadlocks = h.deadlocks;
     st.out_of_model = h.out_of_model;
     st.probes = h.probes;
-    st.dcache_hits = h.dcache_hits;
     st.levels = E.widths.size();
     st.gpu_ms_total = total_ms;
     st.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     st.table_slots = E.table_slots;
+    st.slot_bytes = SLOT_BYTES;
     st.max_states = E.max_states;
     st.complete = (!err && !stopped) ? 1 : 0;
     if (E.timing) accumulate_timing(E, st);
@@ -1483,7 +1551,6 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "count_actions", &b)) E.count_actions = b;
   if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
   if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
-  if (json_num(options_json, "dcache_log2", &d)) E.dcache_log2 = (int)d;
   if (json_bool(options_json, "one_phase", &b)) E.one_phase = b;
   if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
@@ -1509,7 +1576,6 @@ void kmcm_destroy(kmcm_ctx* c) {
   cudaFree(E.store);
   cudaFree(E.parent);
   cudaFree(E.cand);
-  cudaFree(E.dcache);
   cudaFree(E.recv);
   if (E.peers_open)
     for (uint32_t r = 0; r < E.world; ++r)
@@ -1534,7 +1600,7 @@ int kmcm_model_info(const kmcm_ctx*, kmc_model_info_t* out) {
   out->num_init = M::NUM_INIT;
   out->max_fanout = M::MAX_FANOUT;
   out->check_deadlock = M::CHECK_DEADLOCK;
-  out->exact = EXACT64 ? 1 : 0;
+  out->exact = EXACT_SET ? 1 : 0;
   strncpy(out->name, KMC_MODEL_NAME, sizeof(out->name) - 1);
   strncpy(out->digest, KMC_MODEL_DIGEST, sizeof(out->digest) - 1);
   return KMC_OK;
@@ -1637,7 +1703,7 @@ static int fpset_call(kmcm_ctx* c, const uint64_t* fps, size_t n, uint8_t* out, 
   CK(cudaMalloc(&d_fps, n * 8));
   CK(cudaMalloc(&d_out, n));
   CK(cudaMemcpyAsync(d_fps, fps, n * 8, cudaMemcpyHostToDevice, E.stream));
-  k_fpset_put<<<grid_for(E, n, 256, 8), 256, 0, E.stream>>>(E.table, (E.table_slots >> 2) - 1, d_fps, n, d_out, E.ctr, insert);
+  k_fpset_put<<<grid_for(E, n, 256, 8), 256, 0, E.stream>>>(E.table, E.table_slots / BUCKET_SLOTS - 1, d_fps, n, d_out, E.ctr, insert);
   CK(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, E.stream));
   CK(cudaStreamSynchronize(E.stream));
   cudaFree(d_fps);
@@ -1746,8 +1812,8 @@ int kmcm_shard_level_done(kmcm_ctx* c, uint64_t* level_first, uint64_t* level_co
     E.stats.deadlocks = h.deadlocks;
     E.stats.out_of_model = h.out_of_model;
     E.stats.probes = h.probes;
-    E.stats.dcache_hits = h.dcache_hits;
     E.stats.table_slots = E.table_slots;
+    E.stats.slot_bytes = SLOT_BYTES;
     E.stats.max_states = E.max_states;
     if (E.level_count) E.widths.push_back(E.level_count);
     E.stats.levels = E.stats.depth = E.widths.size();

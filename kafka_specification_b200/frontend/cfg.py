@@ -16,6 +16,15 @@ valid TLC configuration:
 
     \\* kspec: LAYOUT LayoutOk                    operator whose conjuncts give each variable's type
     \\* kspec: CAPACITY leaderAndIsrRequests = MaxLeaderEpoch + 1
+    \\* kspec: TYPE leaderAndIsrRequests \\subseteq [leaderEpoch : 0 .. MaxLeaderEpoch, ...]
+                                                  layout type of one variable, overriding the one inferred from the
+                                                  type invariant (a checked hint: a value outside it traps)
+    \\* kspec: KEYED leaderAndIsrRequests BY leaderEpoch
+                                                  a set of records in which the field determines the record: stored as
+                                                  one entry per key value (checked: a second record with the key traps)
+    \\* kspec: PREFIX replicaLog records endOffset
+                                                  in every record of the variable, `records[o]` is the Nil alternative
+                                                  exactly for o >= `endOffset` (checked), so Nil needs no code of its own
 """
 from __future__ import annotations
 
@@ -54,6 +63,9 @@ class Config:
     check_deadlock: bool = True
     layout: str | None = None                                        # kspec pragma
     capacities: dict[str, str] = field(default_factory=dict)         # var -> TLA+ expression text
+    type_hints: dict[str, tuple] = field(default_factory=dict)       # var -> ("\\in" | "\\subseteq", TLA+ expression text)
+    keyed: dict[str, str] = field(default_factory=dict)              # var -> key field
+    prefix: dict[str, tuple] = field(default_factory=dict)           # var -> (array field, length field)
     source: str = ""
 
 
@@ -177,6 +189,18 @@ def parse_cfg(text: str) -> Config:
         m = re.match(r"CAPACITY\s+(\w+)\s*=\s*(.+)$", p)
         if m:
             cfg.capacities[m.group(1)] = m.group(2).strip()
+            continue
+        m = re.match(r"TYPE\s+(\w+)\s*(\\in|\\subseteq)\s+(.+)$", p)
+        if m:
+            cfg.type_hints[m.group(1)] = (m.group(2), m.group(3).strip())
+            continue
+        m = re.match(r"KEYED\s+(\w+)\s+BY\s+(\w+)\s*$", p)
+        if m:
+            cfg.keyed[m.group(1)] = m.group(2)
+            continue
+        m = re.match(r"PREFIX\s+(\w+)\s+(\w+)\s+(\w+)\s*$", p)
+        if m:
+            cfg.prefix[m.group(1)] = (m.group(2), m.group(3))
             continue
         raise CfgError(f"cfg: unknown kspec pragma {p!r}")
     return cfg

@@ -970,6 +970,11 @@ class Lowerer:
             return SSet([(self.b_and([g, self.member(x, b)]), x) for g, x in self.set_items(a)],
                         distinct=isinstance(a, (frozenset, SLazy)) or getattr(a, "distinct", False))
         if op == "\\":
+            if isinstance(a, SLazy) and isinstance(b, frozenset) and a.kind in ("powerset", "recset", "union"):
+                try:
+                    a = frozenset(self.enumerate_lazy(a))          # e.g. (SUBSET Replicas) \\ {{}} in a type expression
+                except LowerError:
+                    pass
             if isinstance(a, frozenset) and isinstance(b, frozenset):
                 return a - b
             return SSet([(self.b_and([g, self.b_not(self.member(x, b))]), x) for g, x in self.set_items(a)],

@@ -13,6 +13,11 @@ TRec / TFn      product of the members: separate atoms at top level, mixed radix
 TSet bitmap     one bit per possible element (element code = bit index)
 TSet array      count + ``cap`` element codes kept sorted ascending, unused slots 0 -> canonical, so
                 equal sets pack to equal bits (leaderAndIsrRequests, KafkaReplication.tla:66)
+TKeyedSet       set of records in which one field (the key) determines the record (checked): one entry per key
+                value, 0 = absent, c + 1 = mixed-radix code c of the other fields  (``\\* kspec: KEYED v BY f``)
+TPrefixFn       function over 0..n-1 into X \\union {Nil} whose Nil entries are exactly those at index >= a sibling
+                length field (checked; FiniteReplicatedLog.tla:84-87 states it): only X is coded
+                (``\\* kspec: PREFIX v arrayField lengthField``)
 
 Every type offers the same operations in two worlds: ``py_*`` on Python values (Init states,
 decoding traces, tests) and ``read``/``write``/``enc``/``dec`` on symbolic values, emitting C.
@@ -30,11 +35,12 @@ def bits_for(card: int) -> int:
 
 
 class Atom:
-    __slots__ = ("index", "path", "bits", "word", "shift")
+    __slots__ = ("index", "path", "bits", "word", "shift", "card")
 
-    def __init__(self, index, path, bits):
+    def __init__(self, index, path, bits, card=None):
         self.index, self.path, self.bits = index, path, bits
         self.word = self.shift = 0
+        self.card = card if card is not None else (1 << bits)     # number of codes a valid state can hold
 
     @property
     def mask(self) -> int:
@@ -49,10 +55,10 @@ class Layout:
         self.words = 0
         self.bits = 0
 
-    def new_atom(self, path: str, bits: int) -> Atom:
+    def new_atom(self, path: str, bits: int, card: int | None = None) -> Atom:
         if bits > 32:
             raise LowerError(f"atom {path} needs {bits} bits (> 32)")
-        a = Atom(len(self.atoms), path, bits)
+        a = Atom(len(self.atoms), path, bits, card)
         self.atoms.append(a)
         return a
 
@@ -64,7 +70,29 @@ class Layout:
             a.word, a.shift = word, used
             used += a.bits
             self.bits += a.bits
+        if word + 1 > max(1, -(-self.bits // 64)):
+            # declaration order wastes a word (atoms never straddle words): first-fit decreasing over the bit
+            # widths, declaration order among equals -- e.g. the 128-bit Kafka layout fits two words exactly
+            fill: list[int] = []
+            place = {}
+            for a in sorted(self.atoms, key=lambda a: (-a.bits, a.index)):
+                for w, u in enumerate(fill):
+                    if u + a.bits <= 64:
+                        break
+                else:
+                    fill.append(0)
+                    w = len(fill) - 1
+                place[a.index] = (w, fill[w])
+                fill[w] += a.bits
+            if len(fill) < word + 1:
+                for a in self.atoms:
+                    a.word, a.shift = place[a.index]
+                word = len(fill) - 1
         self.words = word + 1
+        # can the packed words of a valid state be all ones?  (No, as soon as one field cannot hold its top code
+        # or a word has unused high bits: the engine then uses all-ones as the empty marker of its exact set.)
+        last_used = sum(a.bits for a in self.atoms if a.word == word)
+        self.all_ones_possible = all(a.card == (1 << a.bits) for a in self.atoms) and last_used == 64
 
     # -- python-side packing -------------------------------------------------
     def py_pack(self, state: dict) -> list[int]:
@@ -146,7 +174,7 @@ class Ty:
 
     def _alloc_scalar(self, lay: Layout, path: str):
         b = bits_for(self.card)
-        self.atom = lay.new_atom(path, b) if b > 0 else None
+        self.atom = lay.new_atom(path, b, self.card) if b > 0 else None
 
 
 class TInt(Ty):
@@ -300,6 +328,26 @@ class TRec(Ty):
         for f, t in self.fields.items():
             t.alloc(lay, f"{path}.{f}")
 
+    def apply_prefix(self, arr: str, length: str):
+        """``fields[arr]`` (a function over 0..n-1 into X \\union {nil}) becomes a TPrefixFn governed by ``fields[length]``."""
+        ft, lt = self.fields.get(arr), self.fields.get(length)
+        if not isinstance(ft, TFn) or not isinstance(lt, TInt):
+            raise LowerError(f"PREFIX needs a function field {arr} and an integer field {length}")
+        if list(ft.keys) != list(range(len(ft.keys))):
+            raise LowerError(f"PREFIX: the domain of {arr} must be 0..n-1")
+        u = ft.elems[0]
+        if not isinstance(u, TUnion) or len(u.alts) != 2 or sorted(t.card == 1 for t in u.alts) != [False, True]:
+            raise LowerError(f"PREFIX: {arr} must map into X \\union {{Nil}} with a single Nil value")
+        nil_t = next(t for t in u.alts if t.card == 1)
+        inner_t = next(t for t in u.alts if t.card != 1)
+        pf = TPrefixFn(ft.keys, inner_t, nil_t.py_dec(0), length)
+        # the length field must be read / written before the array
+        order = [f for f in self.fields if f != arr]
+        order.insert(order.index(length) + 1, arr)
+        self.fields = {f: (pf if f == arr else self.fields[f]) for f in order}
+        self.card = 0
+        self._sig = None
+
     def _get(self, v, f):
         if isinstance(v, FnVal):
             return v.apply(f)
@@ -330,10 +378,16 @@ class TRec(Ty):
         if not isinstance(v, FnVal) or set(v.domain()) != set(self.fields):
             raise LowerError(f"value {fmt(v)} is not a record with fields {list(self.fields)}")
         for f, t in self.fields.items():
-            t.py_write(v.apply(f), codes)
+            if isinstance(t, TPrefixFn):
+                t.py_write_len(v.apply(f), v.apply(t.len_field), codes)
+            else:
+                t.py_write(v.apply(f), codes)
 
     def py_read(self, codes):
-        return FnVal({f: t.py_read(codes) for f, t in self.fields.items()})
+        d = {}
+        for f, t in self.fields.items():
+            d[f] = t.py_read_len(codes, d[t.len_field]) if isinstance(t, TPrefixFn) else t.py_read(codes)
+        return FnVal(d)
 
     def enc(self, lw, v):
         if is_const(v):
@@ -362,7 +416,14 @@ class TRec(Ty):
         return SRec(out)
 
     def read(self, lw):
-        return SRec({f: lw.read_ty(t) for f, t in self.fields.items()})
+        d = {}
+        for f, t in self.fields.items():
+            if isinstance(t, TPrefixFn):
+                d[f] = t.read_len(lw, d[t.len_field])
+                lw.read_cache[id(t)] = d[f]
+            else:
+                d[f] = lw.read_ty(t)
+        return SRec(d)
 
     def write(self, lw, v, out):
         if isinstance(v, SUnion):
@@ -370,6 +431,10 @@ class TRec(Ty):
         self._check(v)
         for f, t in self.fields.items():
             x = self._get(v, f)
+            if isinstance(t, TPrefixFn):
+                newlen = self._get(v, t.len_field)
+                t.write_len(lw, x, newlen, newlen is not lw.read_cache.get(id(self.fields[t.len_field])), out)
+                continue
             if x is lw.read_cache.get(id(t)):
                 continue                      # member untouched since it was read
             t.write(lw, x, out)
@@ -537,11 +602,13 @@ class TUnion(Ty):
 class TSet(Ty):
     """Set of ``elem``; bitmap over element codes, or sorted bounded array when ``cap`` is given."""
 
-    def __init__(self, elem: Ty, cap: int | None = None):
+    def __init__(self, elem: Ty, cap: int | None = None, nonempty: bool = False):
         if not elem.card:
             raise LowerError("set element type must be scalar-codeable")
         self.elem, self.cap = elem, cap
-        self.card = (1 << elem.card) if (cap is None and elem.card <= 30) else 0
+        # nonempty: the type excludes {} (checked); as a scalar code the bitmap is stored minus one
+        self.nonempty = bool(nonempty) and cap is None
+        self.card = ((1 << elem.card) - (1 if self.nonempty else 0)) if (cap is None and elem.card <= 30) else 0
         self.chunks: list[Atom] = []
         self.count_atom = None
         self.slots: list[Atom] = []
@@ -554,6 +621,8 @@ class TSet(Ty):
         d = {"t": "set", "elem": self.elem.describe(), "repr": "bitmap" if self.cap is None else "array"}
         if self.cap is not None:
             d["cap"] = self.cap
+        if self.nonempty:
+            d["nonempty"] = True
         return d
 
     def alloc(self, lay, path):
@@ -565,9 +634,9 @@ class TSet(Ty):
                 n -= b
                 i += 1
         else:
-            self.count_atom = lay.new_atom(f"{path}#count", bits_for(self.cap + 1))
+            self.count_atom = lay.new_atom(f"{path}#count", bits_for(self.cap + 1), self.cap + 1)
             eb = bits_for(self.elem.card)
-            self.slots = [lay.new_atom(f"{path}#slot{i}", eb) for i in range(self.cap)]
+            self.slots = [lay.new_atom(f"{path}#slot{i}", eb, self.elem.card) for i in range(self.cap)]
 
     # python
     def _py_codes(self, v) -> list[int]:
@@ -581,15 +650,23 @@ class TSet(Ty):
         m = 0
         for c in self._py_codes(v):
             m |= 1 << c
+        if self.nonempty:
+            if m == 0:
+                raise LowerError("empty set stored in a non-empty set layout")
+            m -= 1
         return m
 
     def py_dec(self, code):
         if not self.card:
             return super().py_dec(code)
+        if self.nonempty:
+            code += 1
         return frozenset(self.elem.py_dec(j) for j in range(self.elem.card) if (code >> j) & 1)
 
     def py_write(self, v, codes):
         cs = self._py_codes(v)
+        if self.nonempty and not cs:
+            raise LowerError("empty set stored in a non-empty set layout")
         if self.cap is None:
             for i, a in enumerate(self.chunks):
                 codes[a.index] = sum(1 << (c - 32 * i) for c in cs if 32 * i <= c < 32 * i + a.bits)
@@ -616,11 +693,17 @@ class TSet(Ty):
             return super().enc(lw, v)
         if is_const(v):
             return str(self.py_enc(v))
-        return self._bitmap_exprs(lw, v, 1)[0]
+        bm = self._bitmap_exprs(lw, v, 1)[0]
+        if self.nonempty:
+            lw.trap_unless(SBool(f"({bm} != 0u)"))
+            return lw.tmp_int(f"((int){bm} - 1)")
+        return bm
 
     def dec(self, lw, code):
         if not self.card:
             return super().dec(lw, code)
+        if self.nonempty:
+            code = lw.tmp_uint(f"((unsigned){code} + 1u)")
         return SSet([(SBool(f"(({code} >> {j}) & 1u)"), self.elem.py_dec(j)) for j in range(self.elem.card)], distinct=True)
 
     def _items(self, lw, v):
@@ -674,7 +757,10 @@ class TSet(Ty):
                 for a in self.chunks:
                     out[a.index] = f"{codes[a.index]}u"
                 return
-            for a, e in zip(self.chunks, self._bitmap_exprs(lw, v, len(self.chunks))):
+            exprs = self._bitmap_exprs(lw, v, len(self.chunks))
+            if self.nonempty:
+                lw.trap_unless(lw.b_or([SBool(f"({e} != 0u)") for e in exprs]))
+            for a, e in zip(self.chunks, exprs):
                 out[a.index] = e
             return
         if is_const(v):
@@ -704,3 +790,235 @@ class TSet(Ty):
         for r, a in enumerate(self.slots):
             terms = [f"(({ps[i]} && {ranks[i]} == {r}) ? {cs[i]} : 0)" for i in range(len(items))]
             out[a.index] = lw.tmp_int("(" + " | ".join(terms) + ")") if terms else "0"
+
+
+class TKeyedSet(Ty):
+    """Set of records in which the field ``key`` determines the record -- a functional dependency the spec
+    maintains and the generated code checks (a second, different record with an existing key traps
+    KMC_FAIL_LAYOUT).  One entry per key value: 0 = no record with that key, c + 1 = code c of the other
+    fields.  Compared with the sorted array this needs no count, no re-sorting on insert and no division to
+    decode, and every element read from it has a CONSTANT key (leaderAndIsrRequests, KafkaReplication.tla:66,
+    138-146: every request carries a fresh leaderEpoch)."""
+
+    def __init__(self, elem: "TRec", key: str):
+        if not isinstance(elem, TRec) or key not in elem.fields:
+            raise LowerError(f"KEYED: the set elements must be records with a field {key}")
+        self.elem, self.key = elem, key
+        self.key_ty = elem.fields[key]
+        self.rest = TRec({f: t for f, t in elem.fields.items() if f != key})
+        if not self.key_ty.card or not self.rest.card:
+            raise LowerError("KEYED: key and remaining fields must be scalar-codeable")
+        self.card = 0
+        self.atom = None
+        self.entries: list[Atom] = []
+
+    def kind(self):
+        return "set"
+
+    def describe(self):
+        return {"t": "set", "repr": "keyed", "key": self.key, "elem": self.elem.describe()}
+
+    def alloc(self, lay, path):
+        b = bits_for(self.rest.card + 1)
+        self.entries = [lay.new_atom(f"{path}#{self.key}={fmt(self.key_ty.py_dec(j))}", b, self.rest.card + 1)
+                        for j in range(self.key_ty.card)]
+
+    def _rest_of(self, v):
+        if isinstance(v, FnVal):
+            return FnVal({f: v.apply(f) for f in self.rest.fields})
+        return SRec({f: v.fields[f] for f in self.rest.fields})
+
+    # python
+    def py_write(self, v, codes):
+        if not isinstance(v, frozenset):
+            raise LowerError(f"value {fmt(v)} is not a set")
+        for a in self.entries:
+            codes[a.index] = 0
+        for x in v:
+            if not isinstance(x, FnVal) or set(x.domain()) != set(self.elem.fields):
+                raise LowerError(f"value {fmt(x)} is not a record with fields {list(self.elem.fields)}")
+            a = self.entries[self.key_ty.py_enc(x.apply(self.key))]
+            c = self.rest.py_enc(self._rest_of(x)) + 1
+            if codes[a.index] not in (0, c):
+                raise LowerError(f"two records with {self.key} = {fmt(x.apply(self.key))} in a KEYED set")
+            codes[a.index] = c
+
+    def py_read(self, codes):
+        out = []
+        for j, a in enumerate(self.entries):
+            c = codes[a.index]
+            if c:
+                d = dict(self.rest.py_dec(c - 1).items)
+                d[self.key] = self.key_ty.py_dec(j)
+                out.append(FnVal({f: d[f] for f in self.elem.fields}))
+        return frozenset(out)
+
+    # symbolic
+    def _entry_sig(self):
+        return "keyed-entry:" + self.rest.sig()
+
+    def read(self, lw):
+        items = []
+        for j, a in enumerate(self.entries):
+            g = SBool(f"(a{a.index} != 0u)")
+            rv = self.rest.dec(lw, lw.tmp_int(f"((int)a{a.index} - 1)"))
+            d = dict(rv.fields)
+            d[self.key] = self.key_ty.py_dec(j)
+            x = SRec({f: d[f] for f in self.elem.fields})
+            lw.enc_cache[id(x)] = (self._entry_sig(), x, f"a{a.index}", lw.cg.blocks[-1], lw.unit_id)
+            items.append((g, x))
+        return SSet(items, distinct=True)
+
+    def write(self, lw, v, out):
+        if is_const(v):
+            codes: dict = {}
+            self.py_write(v, codes)
+            for a in self.entries:
+                out[a.index] = str(codes[a.index])
+            return
+        if isinstance(v, frozenset):
+            items = [(True, x) for x in sorted(v, key=sort_key)]
+        elif isinstance(v, SSet):
+            items = v.items
+        else:
+            raise LowerError(f"cannot store {v!r} in a set field")
+        contrib: list[list] = [[] for _ in self.entries]          # per entry: (match guard, entry code expr)
+        for g, x in items:
+            if isinstance(x, SUnion):
+                x = lw.narrow_union(x, self.elem.kind())
+            kx = x.apply(self.key) if isinstance(x, FnVal) else x.fields[self.key]
+            hit = lw._code_hit(x)
+            if hit is not None and hit[0] == self._entry_sig():
+                code = hit[2]                                     # an element read from this layout: its entry as is
+            else:
+                code = lw.tmp_int(f"({lw.encode(self.rest, self._rest_of(x))} + 1)")
+            if is_const(kx):
+                try:
+                    js = [(self.key_ty.py_enc(kx), g)]
+                except LowerError:
+                    lw.trap_unless(lw.b_not(g))
+                    continue
+            else:
+                js = []
+                covered = []
+                for j in range(self.key_ty.card):
+                    m = lw.eq(kx, self.key_ty.py_dec(j))
+                    if m is not False:
+                        js.append((j, lw.b_and([g, m])))
+                        covered.append(m)
+                in_range = (isinstance(kx, SInt) and isinstance(self.key_ty, TInt) and
+                            self.key_ty.lo <= kx.lo and kx.hi <= self.key_ty.hi)
+                if not in_range:
+                    lw.trap_unless(lw.b_or([lw.b_not(g)] + covered))   # a key outside the layout's key range
+            for j, m in js:
+                if m is not False:
+                    contrib[j].append((m, code))
+        for a, lst in zip(self.entries, contrib):
+            for i in range(len(lst)):
+                for k in range(i):
+                    (m1, c1), (m2, c2) = lst[k], lst[i]
+                    if c1 != c2:                                    # two different records with this key: not a function
+                        lw.trap_unless(lw.b_not(lw.b_and([m1, m2, SBool(f"({c1} != {c2})")])))
+            terms = [c if m is True else f"({lw.bstr(m)} ? {c} : 0)" for m, c in lst]
+            out[a.index] = lw.tmp_int("(" + " | ".join(terms) + ")") if terms else "0"
+
+
+class TPrefixFn(Ty):
+    """``[0..n-1 -> X \\union {nil}]`` whose entries are nil exactly at the indexes >= the record's length field
+    (FiniteReplicatedLog.tla:84-87 states this as part of TypeOk; the generated code re-checks it whenever a
+    record is written).  Only X is stored: ``bits_for(card X)`` per entry, unwritten entries hold 0."""
+
+    def __init__(self, keys: list, inner: Ty, nil, len_field: str):
+        import copy
+        self.keys = list(keys)
+        self.inner = [copy.deepcopy(inner) for _ in keys]
+        self.nil, self.len_field = nil, len_field
+        self.card = 0
+        self.atom = None
+
+    def kind(self):
+        return "fn"
+
+    def describe(self):
+        return {"t": "prefixfn", "keys": [fmt(k) for k in self.keys], "inner": self.inner[0].describe(),
+                "nil": fmt(self.nil), "len": self.len_field}
+
+    def alloc(self, lay, path):
+        for k, t in zip(self.keys, self.inner):
+            t._alloc_scalar(lay, f"{path}[{fmt(k)}]")
+
+    # python
+    def py_write_len(self, v, length, codes):
+        if not isinstance(v, FnVal) or set(v.domain()) != set(self.keys):
+            raise LowerError(f"function domain mismatch storing {fmt(v)}")
+        for k, t in zip(self.keys, self.inner):
+            x = v.apply(k)
+            is_nil = kind_sig(x) == kind_sig(self.nil) and x == self.nil
+            if is_nil != (k >= length):
+                raise LowerError(f"PREFIX layout violated: entry {k} of {fmt(v)} with length {length}")
+            if t.atom is not None:
+                codes[t.atom.index] = 0 if is_nil else t.py_enc(x)
+
+    def py_read_len(self, codes, length):
+        return FnVal({k: (t.py_dec(codes[t.atom.index] if t.atom is not None else 0) if k < length else self.nil)
+                      for k, t in zip(self.keys, self.inner)})
+
+    def py_write(self, v, codes):
+        raise LowerError("internal: TPrefixFn is written through its record")
+
+    def py_read(self, codes):
+        raise LowerError("internal: TPrefixFn is read through its record")
+
+    # symbolic
+    def read_len(self, lw, length):
+        vals = []
+        for k, t in zip(self.keys, self.inner):
+            g = lw.cmp("<", k, length)
+            if t.atom is None:
+                x = t.py_dec(0)
+            else:
+                x = t.dec(lw, f"a{t.atom.index}")
+                lw.remember_code(t, x, f"a{t.atom.index}")
+            if g is True:
+                vals.append(x)
+            elif g is False:
+                vals.append(self.nil)
+            else:
+                # same alternative order as TUnion.dec: sorted by kind
+                alts = sorted([(lw.b_not(g), self.nil), (g, x)], key=lambda a: kind_sig(a[1]))
+                vals.append(SUnion(alts))
+        self._read_vals = vals
+        return SFn(self.keys, vals)
+
+    def write_len(self, lw, v, newlen, len_changed: bool, out):
+        if isinstance(v, FnVal):
+            m = dict(v.items)
+        elif isinstance(v, SFn):
+            m = dict(zip(v.keys, v.vals))
+        else:
+            raise LowerError(f"cannot store {v!r} in a function layout")
+        if set(m) != set(self.keys):
+            raise LowerError("function domain mismatch")
+        old = getattr(self, "_read_vals", [None] * len(self.keys))
+        nil_kind = kind_sig(self.nil)
+        for i, (k, t) in enumerate(zip(self.keys, self.inner)):
+            x = m[k]
+            untouched = x is old[i]
+            if untouched and not len_changed:
+                continue
+            if is_const(x):
+                nil_g = kind_sig(x) == nil_kind and x == self.nil
+            elif isinstance(x, SUnion):
+                nil_g = lw.b_or([lw.b_and([g, lw.eq(a, self.nil)]) for g, a in x.alts if kind_sig(a) == nil_kind])
+            else:
+                nil_g = False if kind_sig(x) != nil_kind else lw.eq(x, self.nil)
+            expect_nil = lw.cmp(">=", k, newlen)
+            lw.trap_unless(lw.b_or([lw.b_and([nil_g, expect_nil]), lw.b_and([lw.b_not(nil_g), lw.b_not(expect_nil)])]))
+            if untouched or t.atom is None:
+                continue
+            if nil_g is True:
+                out[t.atom.index] = "0"
+                continue
+            xv = lw.narrow_union(x, t.kind()) if isinstance(x, SUnion) else x
+            c = lw.encode(t, xv)
+            out[t.atom.index] = c if expect_nil is False else lw.tmp_int(f"({lw.bstr(expect_nil)} ? 0 : {c})")

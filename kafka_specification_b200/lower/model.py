@@ -113,7 +113,7 @@ class TypeInference:
                 parts.append(L.TFn(dom, [self.type_from_setval(frozenset(r.apply(k) for r in recs)) for k in dom]))
         if sets:
             universe = frozenset().union(*sets)
-            parts.append(L.TSet(self.type_from_setval(universe)))
+            parts.append(L.TSet(self.type_from_setval(universe), nonempty=frozenset() not in sets))
         if len(bools) + len(ints) + len(atoms) + len(recs) + len(sets) != len(v):
             raise LowerError("unsupported element kind in a layout type")
         return parts[0] if len(parts) == 1 else L.TUnion(sorted(parts, key=lambda t: t.kind()))
@@ -490,6 +490,7 @@ HEADER_PROLOGUE = """\
 namespace kmc_model {{
 static constexpr int W = {words};
 static constexpr int STATE_BITS = {bits};
+static constexpr bool ALL_ONES_POSSIBLE = {all_ones};   /* can a valid state pack to all-ones words? */
 static constexpr int NUM_ACTIONS = {num_actions};
 static constexpr int NUM_INVARIANTS = {num_invariants};
 static constexpr int NUM_CONSTRAINTS = {num_constraints};
@@ -520,15 +521,41 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
     ti.collect(d.body, dctx, d.module, {})
     lay = L.Layout()
     lay.variables = list(lw.variables)
+    def apply_prefix(ty, arr, length):
+        if isinstance(ty, L.TFn):
+            for t in ty.elems:
+                apply_prefix(t, arr, length)
+            ty.card = 0
+            ty._sig = None
+        elif isinstance(ty, L.TRec):
+            ty.apply_prefix(arr, length)
+        else:
+            raise LowerError("PREFIX applies to a record variable or a function of records")
+
     for v in lw.variables:
-        ty = copy.deepcopy(ti.variable_type(v))
-        if v in cfg.capacities:
+        if v in cfg.type_hints:
+            # checked hint: the layout type of this variable as written in the cfg (narrower than the type
+            # invariant states, e.g. request epochs are never Nil); a value outside it traps at run time
+            op, text = cfg.type_hints[v]
+            sv = lw.ev(parse_expression_text(text), root, None, {}, None)
+            ty = ti.type_from_setval(sv)
+            if op == "\\subseteq":
+                ty = L.TSet(ty)
+        else:
+            ty = copy.deepcopy(ti.variable_type(v))
+        if v in cfg.keyed:
+            if not isinstance(ty, L.TSet):
+                raise LowerError(f"KEYED given for {v}, which is not a set")
+            ty = L.TKeyedSet(ty.elem, cfg.keyed[v])
+        elif v in cfg.capacities:
             if not isinstance(ty, L.TSet):
                 raise LowerError(f"CAPACITY given for {v}, which is not a set")
             cap = lw.ev(parse_expression_text(cfg.capacities[v]), root, None, {}, None)
             if not is_int_const(cap) or cap < 0:
                 raise LowerError(f"CAPACITY {v} does not evaluate to a natural number")
             ty = L.TSet(ty.elem, cap)
+        if v in cfg.prefix:
+            apply_prefix(ty, *cfg.prefix[v])
         lay.var_types[v] = ty
         ty.alloc(lay, v)
     lay.finish()
@@ -651,6 +678,7 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
 
     parts = [HEADER_PROLOGUE.format(
         name=name, module=module, digest=body_digest, words=lay.words, bits=lay.bits,
+        all_ones="true" if lay.all_ones_possible else "false",
         num_actions=max(1, len(lw.actions)), num_invariants=len(cfg.invariants),
         num_constraints=len(cfg.constraints), num_init=len(init_words), max_fanout=max(1, max_fanout),
         check_deadlock="true" if cfg.check_deadlock else "false")]

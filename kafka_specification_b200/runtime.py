@@ -40,7 +40,7 @@ class Stats(ctypes.Structure):
         ("gpu_ms_total", ctypes.c_double), ("gpu_ms_expand", ctypes.c_double), ("gpu_ms_insert", ctypes.c_double),
         ("launches_expand", ctypes.c_uint64), ("launches_insert", ctypes.c_uint64), ("launches_other", ctypes.c_uint64),
         ("wall_ms", ctypes.c_double), ("table_slots", ctypes.c_uint64), ("max_states", ctypes.c_uint64),
-        ("complete", ctypes.c_uint64), ("gpu_ms_invariant", ctypes.c_double), ("dcache_hits", ctypes.c_uint64),
+        ("complete", ctypes.c_uint64), ("gpu_ms_invariant", ctypes.c_double), ("slot_bytes", ctypes.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -169,7 +169,7 @@ class StateDecoder:
         if k == "union":
             return sum(self._card(a) for a in t["alts"])
         if k == "set":
-            return 1 << self._card(t["elem"])
+            return (1 << self._card(t["elem"])) - (1 if t.get("nonempty") else 0)
         raise ValueError(k)
 
     def _dec(self, t, code: int):
@@ -204,16 +204,46 @@ class StateDecoder:
             raise ValueError("bad union code")
         if k == "set":
             c = self._card(t["elem"])
+            if t.get("nonempty"):
+                code += 1
             return frozenset(self._dec(t["elem"], j) for j in range(c) if (code >> j) & 1)
         raise ValueError(k)
 
     def _read(self, t, codes: list[int], pos: list[int]):
         k = t["t"]
         if k == "rec":
-            return FnVal({f: self._read(ft, codes, pos) for f, ft in t["fields"].items()})
+            d = {}
+            for f, ft in t["fields"].items():
+                if ft["t"] == "prefixfn":
+                    # entries at index >= the record's length field are the nil value; the others hold the inner code
+                    n, vals = d[ft["len"]], {}
+                    for key in ft["keys"]:
+                        kk = _parse_atom(key)
+                        if _bits_for(self._card(ft["inner"])) == 0:
+                            x = self._dec(ft["inner"], 0)
+                        else:
+                            x = self._dec(ft["inner"], codes[pos[0]])
+                            pos[0] += 1
+                        vals[kk] = x if kk < n else _parse_atom(ft["nil"])
+                    d[f] = FnVal(vals)
+                else:
+                    d[f] = self._read(ft, codes, pos)
+            return FnVal(d)
         if k == "fn":
             return FnVal({_parse_atom(key): self._read(t["elem"], codes, pos) for key in t["keys"]})
         if k == "set":
+            if t["repr"] == "keyed":
+                key, fields = t["key"], t["elem"]["fields"]
+                rest = {"t": "rec", "fields": {f: ft for f, ft in fields.items() if f != key}}
+                out = []
+                for j in range(self._card(fields[key])):
+                    c = codes[pos[0]]
+                    pos[0] += 1
+                    if c:
+                        d = dict(self._dec(rest, c - 1).items)
+                        d[key] = self._dec(fields[key], j)
+                        out.append(FnVal({f: d[f] for f in fields}))
+                return frozenset(out)
             ecard = self._card(t["elem"])
             if t["repr"] == "bitmap":
                 out, base, n = [], 0, ecard

@@ -239,17 +239,6 @@ def test_candidate_overflow_is_an_error_not_a_wrong_answer():
         assert ck.run().distinct == 29791
 
 
-@pytest.mark.parametrize("name", ["kip320_small", "asyncisr_small", "frl_3x4x2"])
-def test_duplicate_filter_does_not_change_the_result(name, goldens):
-    """The L2-resident duplicate filter in front of the set only short-cuts probes of fingerprints the set holds."""
-    g = goldens[name]
-    with checker(name, dcache_log2=16, cont=True) as ck:
-        r = ck.run()
-    assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
-        g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
-    assert r.stats["dcache_hits"] > 0
-
-
 def test_scatter_rounds_when_a_tile_enables_more_pairs_than_the_list_holds(goldens):
     """FiniteReplicatedLog enables ~16 successors per state: a 4096-state tile overflows the 12288-entry pair
     list of the expand kernel, which then works through the site segments in several scatter rounds."""

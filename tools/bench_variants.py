@@ -20,7 +20,8 @@ def main():
         v = json.loads(spec)
         tag = v.pop("tag", "run")
         lib = v.pop("lib", "")
-        so, _ = model_paths(name)
+        mdir = v.pop("model", name)                  # lowering variant: its own model directory (<model>@<tag>)
+        so, js = model_paths(mdir)
         if lib:
             so = so[:-3] + "." + lib + ".so"
         opts = dict(v)
@@ -30,7 +31,7 @@ def main():
             opts.setdefault("max_states", int(gold["distinct"] * 1.02) + 4096)
         best = None
         try:
-            with Checker(name, model_lib=so, cont=True, **opts) as ck:
+            with Checker(mdir, model_lib=so, model_json=js, cont=True, **opts) as ck:
                 for _ in range(reps):
                     r = ck.run(raise_on_error=False)
                     st = r.stats
@@ -40,7 +41,7 @@ def main():
                            "distinct": r.distinct, "generated": r.generated, "depth": r.depth,
                            "gpu_ms": round(st["gpu_ms_total"], 3), "expand_ms": round(st["gpu_ms_expand"], 3),
                            "insert_ms": round(st["gpu_ms_insert"], 3), "invariant_ms": round(st["gpu_ms_invariant"], 3),
-                           "probes": st["probes"], "dcache_hits": st["dcache_hits"], "opts": opts}
+                           "probes": st["probes"], "opts": opts}
                     if best is None or row["gpu_ms"] < best["gpu_ms"] or not row["ok"]:
                         best = row
                     if not row["ok"]:
