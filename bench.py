@@ -15,8 +15,12 @@ per-level widths) is compared with the committed golden before a number is print
                kmc_level_widths), wall clock: includes the hash-set reset, the host->device copy of the
                initial states and the per-level device->host counter reads
   roofline     dominant kernel by time, live CUDA-event launch durations (engine stream)
-  cpu_baseline Oracle B (oracle/kspec_oracle.c, "port": TLC itself cannot run here -- no JVM) on
-               the box's host cores, on a bounded prefix of the same BFS
+  e2e_cold     what a tlc2 user pays for a NEW .cfg: parse + lower (measured on the build host, model.json) +
+               nvcc of the lowered model (timed live, on this box) + library load, kmc_create and the first kmc_run
+  cpu_baseline baseline/cpu_bfs.cpp: the SAME lowered Next / invariants compiled for the host (-O3 -march=native),
+               packed states, lock-free 64-bit fingerprint table, persistent worker pool, per-thread output
+               buffers, all host threads -- a full BFS of the same .cfg when it fits the time budget (kind "port":
+               TLC itself cannot run here, no JVM).  Oracle B stays what it is: the checker.
 
 --impl reference times that CPU path alone (rank 0 only).
 """
@@ -113,32 +117,53 @@ def check_result(model, distinct, generated, depth, levels, deadlocks):
     return "bit-exact vs tests/golden/goldens.json (" + "+".join(g["sources"]) + ")"
 
 
-def cpu_sample(model: str, seconds_budget: float = 20.0):
-    """Oracle B on a bounded prefix of the same BFS (the checker; never the thing shipped).
-    The thread count is the best of a few candidates on a short probe, so that the baseline is
-    not penalised by lock/NUMA contention on many-core hosts."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import kso
-    reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
-    if "kso" not in reg:
-        return None
-    kmodel, params = reg["kso"]
+def cpu_run(model: str, threads: int = 0, budget_s: float = 25.0, table_log2: int = 0):
+    """One run of the CPU arm (baseline/cpu_bfs.cpp).  A short bounded probe gives the rate; if the full BFS is
+    expected to fit `budget_s` it is run in full (same_config true, result checked against the golden), else the
+    run is bounded to about budget_s of work."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import cpu_bfs
     cores = os.cpu_count() or 1
-    best_t, best_rate = cores, 0.0
-    for t in sorted({cores, max(1, cores // 2), 32, 16, 8}, reverse=True):
-        if t > cores:
+    threads = threads or cores
+    g = golden_for(model)
+    total = g["distinct"] if g else 0
+    if not table_log2:
+        table_log2 = 20
+        while (1 << table_log2) < 2.5 * max(total, 1 << 18):
+            table_log2 += 1
+    probe = cpu_bfs.run(model, threads, min(table_log2, 26), stop_after_states=2_000_000)
+    rate = probe["distinct"] / max(probe["seconds"], 1e-9)
+    full = bool(total) and (probe["complete"] or total / rate <= budget_s)
+    if probe["complete"]:
+        r = probe
+    else:
+        r = cpu_bfs.run(model, threads, table_log2, stop_after_states=0 if full else int(rate * budget_s))
+    if r["fail"]:
+        raise SystemExit(f"cpu baseline failed on {model}: code {r['fail']}")
+    if r["complete"] and g:
+        got = (r["distinct"], r["generated"], r["depth"], r["deadlocks"], r["levels"])
+        want = (g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+        if got != want:
+            raise SystemExit(f"CPU baseline disagrees with the golden on {model}: {got[:4]} vs {want[:4]}")
+    what = "full BFS" if r["complete"] else f"first {r['distinct']} distinct states ({r['depth']} levels)"
+    return {"value": r["distinct"] / max(r["seconds"], 1e-9), "unit": "states/s", "cores": threads, "kind": "port",
+            "same_config": bool(r["complete"]), "seconds": r["seconds"], "distinct": r["distinct"],
+            "sample": f"baseline/cpu_bfs.cpp (the lowered Next of {model} compiled for the host, packed states, lock-free "
+                      f"64-bit fingerprint table, {threads} of {cores} host threads): {what} in {r['seconds']:.2f} s; "
+                      f"TLC itself unavailable (no JVM)"}
+
+
+def cpu_scaling(model: str):
+    """Bounded samples at 1 and 16 threads (the scaling reference next to the all-threads number)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import cpu_bfs
+    out = {}
+    for t in (1, 16):
+        if t > (os.cpu_count() or 1):
             continue
-        r = kso.run(kmodel, params, threads=t, max_states=3_000_000)
-        rate = r["distinct"] / max(r["seconds"], 1e-9)
-        if rate > best_rate:
-            best_t, best_rate = t, rate
-    cap = int(min(max(best_rate * seconds_budget, 3_000_000), 60_000_000))
-    r = kso.run(kmodel, params, threads=best_t, max_states=cap)
-    return {"value": r["distinct"] / max(r["seconds"], 1e-9), "unit": METRIC, "cores": best_t, "kind": "port",
-            "sample": f"Oracle B (hand-written C restatement), first {r['distinct']} distinct states "
-                      f"({r['depth']} BFS levels) of {model}, {r['seconds']:.1f} s on {best_t} of {cores} host "
-                      f"threads (best of a thread-count probe); TLC itself unavailable (no JVM)",
-            "seconds": r["seconds"], "distinct": r["distinct"]}
+        r = cpu_bfs.run(model, t, 25, stop_after_states=1_500_000 * t)
+        out[str(t)] = round(r["distinct"] / max(r["seconds"], 1e-9))
+    return out
 
 
 def config_for(model: str, extra: dict | None = None) -> dict:
@@ -152,30 +177,54 @@ def config_for(model: str, extra: dict | None = None) -> dict:
 
 
 def run_reference(args):
-    """The reference-side CPU path, all host threads, bounded sample per step."""
+    """The CPU arm alone (rank 0): every step is one run of baseline/cpu_bfs.cpp on all host threads -- the full
+    BFS of the same .cfg when a run fits ~40 s, else a bounded prefix (same_config false)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     vals = []
-    sample = None
     for i in range(args.warmup + args.steps):
-        s = cpu_sample(args.model, seconds_budget=8.0)
+        s = cpu_run(args.model, budget_s=40.0)
         if i >= args.warmup:
             vals.append(s)
-        sample = s
     total_states = sum(v["distinct"] for v in vals)
     total_s = sum(v["seconds"] for v in vals)
     value = total_states / total_s
+    last = vals[-1]
     line = {"metric": METRIC, "value": value, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * total_s / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic (the .cfg is the input)",
-            "impl": "reference", "config": config_for(args.model),
-            "cpu_baseline": {"value": value, "unit": "states/s", "cores": sample["cores"], "kind": "port",
-                             "sample": sample["sample"]},
+            "impl": "reference", "config": config_for(args.model, {"same_config": last["same_config"]}),
+            "cpu_baseline": {"value": value, "unit": "states/s", "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"], "same_config": last["same_config"],
+                             "thread_scaling_states_per_s": cpu_scaling(args.model)},
             "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cold_start(model: str, opts: dict):
+    """A new .cfg, end to end: (parse + lower, measured when the model was lowered on the build host; the .tla
+    sources are not on this box) + nvcc of the lowered header, live + dlopen/kmc_create + the first kmc_run."""
+    from kafka_specification_b200 import build as B
+    from kafka_specification_b200.runtime import Checker
+    meta = load_json(os.path.join(B.model_dir(model), "model.json"))
+    out = os.path.join(ROOT, "build", "cold")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, f"libkmc_{model}.cold.so")
+    t0 = time.perf_counter()
+    B.compile_model_to(model, so)
+    t1 = time.perf_counter()
+    ck = Checker(model, model_lib=so, **opts)
+    r = ck.run()
+    t2 = time.perf_counter()
+    ck.close()
+    lower_s = float(meta.get("lower_seconds", 0.0))
+    total = lower_s + (t2 - t0)
+    return {"seconds": total, "lower_s": lower_s, "nvcc_s": t1 - t0, "load_create_run_s": t2 - t1,
+            "value": r.distinct / total, "unit": "states/s",
+            "note": "lower_s measured on the build host (the .tla sources are not shipped to the GPU box); the rest live"}
 
 
 def run_single(args):
@@ -264,7 +313,8 @@ def run_single(args):
     r_inv = roof("k_invariants", inv_bytes, inv_ms, n_inv)
     ranked = sorted([r_exp, r_ins, r_inv], key=lambda r: -r["share_of_gpu_time"])
     dominant, other = ranked[0], ranked[1:]
-    cpu = cpu_sample(args.model) if not args.no_cpu_baseline else None
+    cpu = cpu_run(args.model) if not args.no_cpu_baseline else None
+    cold = cold_start(args.model, opts) if not args.no_cold else None
     info = ck.info
     depth = res.depth
     line = {
@@ -275,7 +325,8 @@ def run_single(args):
                                           "table_slots": res.stats["table_slots"], "parity": parity,
                                           "exact_fingerprints": bool(info.exact)}),
         "roofline": dominant, "roofline_other": other,
-        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")} if cpu else None,
+        "e2e_cold": cold,
         "e2e": {"value": e2e, "unit": "states/s", "ms_per_step": sum(e2e_ms) / steps,
                 "h2d_bytes_per_step": info.num_init * (W + 1) * 8 + 8 * 16 + (depth + 1) * 64,
                 "d2h_bytes_per_step": (depth + 1) * (17 + 64) * 8 + 18 * 8 + depth * 8},
@@ -380,25 +431,21 @@ def main():
     ap.add_argument("--table-log2", type=int, default=0)
     ap.add_argument("--max-states", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold-start (nvcc + first run) measurement")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-to-all exchange instead of the fused peer-memory path")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    g = golden_for(args.model)
-    if g and not args.max_states:
-        args.max_states = int(g["distinct"] * 1.02) + 1024
-    if g and not args.table_log2:
-        per_rank = g["distinct"] / max(1, int(os.environ.get("WORLD_SIZE", "1")))
-        lg = 20
-        while (1 << lg) < 2.2 * per_rank:
-            lg += 1
-        args.table_log2 = lg
+    # Sizing is configuration (like TLC's -fpmem), not derived from the answer: 2^30 set slots and room for 2^29
+    # states per rank for the headline class of models; an overflow is reported (KMC_E_TABLE_FULL / STORE_FULL).
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not args.table_log2:
+        args.table_log2 = 30 if world == 1 else 29
+    if not args.max_states:
+        args.max_states = (1 << 29) if world == 1 else (1 << 28)
     if args.impl == "reference":
         return run_reference(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        if args.max_states and g:
-            args.max_states = int(g["distinct"] / world * 1.25) + 4096
         return run_sharded(args)
     return run_single(args)
 

@@ -146,6 +146,14 @@ def compile_model(name: str, force: bool = False, verbose_ptxas: bool = True, va
     return so
 
 
+def compile_model_to(name: str, out_so: str) -> str:
+    """Plain nvcc of the prebuilt lowered header into `out_so` (no stamp, no log): the cold-start timing of bench.py."""
+    hdr = os.path.join(model_dir(name), "model.h")
+    _run([nvcc_path(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177",
+          *VARIANTS[""], f"-I{INCLUDE}", "-include", hdr, os.path.join(CSRC, "kmc_engine.cu"), "-o", out_so])
+    return out_so
+
+
 def build_model(module: str, cfg_path: str, name: str, force: bool = False) -> str:
     """Lower (when the .tla sources are reachable) and compile; returns the library path."""
     have_sources = any(os.path.exists(os.path.join(d, module + ".tla")) for d in tla_search_dirs())

@@ -190,6 +190,7 @@ struct Params {
   uint32_t rank, world;
   uint32_t check_deadlock;
   uint32_t count_actions;
+  uint32_t prefetch;        // K1 issues an L2 prefetch of every candidate's first bucket (see flush_stage)
   // fused exchange (world > 1, after kmc_shard_open_peers): every rank's inbox, mapped into this
   // process through CUDA IPC.  An inbox is two buffers (double buffering); a buffer is an 8-word
   // header (rows sent by each source rank) followed by world regions of region_rows rows.
@@ -460,6 +461,18 @@ __device__ __forceinline__ void flush_stage(const Params& p, uint32_t wbuf, uint
     } else {
       uint64_t* dst = p.cand + base * ROW;
       for (unsigned k = lane; k < n * ROW; k += 32) dst[k] = lds64(wbuf + k * 8);      // coalesced
+      if (p.prefetch && !M::HAS_SYMMETRY) {
+        // Software pipelining across kernels through the L2: the bucket this candidate will probe in K2 is
+        // requested now, while K1 still has integer work to hide the DRAM latency behind.  With frontier chunks
+        // sized so that a chunk's buckets fit the 126 MB L2, K2 then probes L2-resident sectors.
+        for (unsigned r = lane; r < n; r += 32) {
+          State t;
+#pragma unroll
+          for (int q = 0; q < W; ++q) t.w[q] = lds64(wbuf + (r * ROW + q) * 8);
+          const char* a = bucket_addr(p.table, bucket_of(fingerprint(t), p.bucket_mask));
+          asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+        }
+      }
     }
   } else {
     for (unsigned r0 = 0; r0 < n; r0 += 32) {
@@ -1044,6 +1057,8 @@ struct Engine {
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
   uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
+  bool prefetch = false;            // K1 prefetches candidate buckets into L2 (pair with a small chunk_states)
+  uint64_t chunk_states_opt = 0;    // frontier states per K1/K2 launch pair (0: as many as the candidate buffer allows)
   bool one_phase = false;           // comparison only: the round-1 one-phase K1 (needs a -DKMC_ONE_PHASE build)
 
   void* table = nullptr;
@@ -1101,6 +1116,7 @@ struct Engine {
     p.world = world;
     p.check_deadlock = check_deadlock ? 1 : 0;
     p.count_actions = count_actions ? 1 : 0;
+    p.prefetch = prefetch ? 1 : 0;
     for (int r = 0; r < MAX_WORLD; ++r) p.peer_inbox[r] = peer_inbox[r];
     p.inbox_stride = inbox_stride;
     p.p2p = 0;
@@ -1238,6 +1254,7 @@ static int engine_alloc(Engine& E) {
   // assumes <= 32 and relies on the kernel's overflow check (KMC_E_CAND_FULL, nothing is lost silently).
   if (E.fanout_bound == 0) E.fanout_bound = std::min<uint32_t>((uint32_t)M::MAX_FANOUT, 32u);
   E.chunk_states = std::max<uint64_t>(1, E.region_rows / E.fanout_bound);
+  if (E.chunk_states_opt) E.chunk_states = std::min<uint64_t>(E.chunk_states, E.chunk_states_opt);
   if (E.own_stream) CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&E.table, E.table_slots * SLOT_BYTES));
   CK(cudaMalloc(&E.store, E.max_states * W * 8));
@@ -1552,6 +1569,8 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_num(options_json, "stop_after_states", &d)) E.stop_after_states = (uint64_t)d;
   if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
   if (json_bool(options_json, "one_phase", &b)) E.one_phase = b;
+  if (json_bool(options_json, "prefetch", &b)) E.prefetch = b;
+  if (json_num(options_json, "chunk_states", &d)) E.chunk_states_opt = (uint64_t)d;
   if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
     // a cudaStream_t handle of the calling process (e.g. torch.cuda.current_stream().cuda_stream): engine

@@ -35,7 +35,9 @@
 #define NONE 255
 #define MAX_SUCC 256
 
-enum { M_IDSEQ = 0, M_FRL = 1, M_TRUNCHW = 2, M_KIP101 = 3, M_KIP279 = 4, M_KIP320 = 5, M_FIRSTTRY = 6, M_ASYNCISR = 7 };
+enum { M_IDSEQ = 0, M_FRL = 1, M_TRUNCHW = 2, M_KIP101 = 3, M_KIP279 = 4, M_KIP320 = 5, M_FIRSTTRY = 6, M_ASYNCISR = 7,
+       M_KIP320_279 = 8 /* Kip320's Next with BecomeFollowerTruncateKip279 swapped in, the experiment Kip320.tla:126-133 suggests */ };
+#define IS_KAFKA(m) (((m) >= M_TRUNCHW && (m) <= M_FIRSTTRY) || (m) == M_KIP320_279)
 enum { INV_WEAKISR = 0, INV_STRONGISR = 1, INV_LEADERINISR = 2, INV_VALIDHW = 3, INV_COUNT = 4 };
 
 /* ------------------------------------------------------------------------------------------
@@ -626,6 +628,17 @@ static void kafka_expand(const Cfg* c, const KState* s, Out* o) {
       fenced_become_follower_and_truncate(c, s, o);
       fenced_follower_fetch(c, s, o);
       break;
+    case M_KIP320_279:   /* Kip320.tla:150-159 with :157 replaced by Kip279.tla:47-51 (models/MCKip320With279.tla) */
+      controller_elect_leader(c, s, o);
+      controller_shrink_isr(c, s, o);
+      become_leader(c, s, o);
+      fenced_leader_expand_isr(c, s, o);
+      fenced_leader_shrink_isr(c, s, o);
+      leader_write(c, s, o);
+      fenced_leader_inc_hw(c, s, o);
+      become_follower_truncate_kip279(c, s, o);
+      fenced_follower_fetch(c, s, o);
+      break;
     case M_FIRSTTRY:  /* Kip320FirstTry.tla:159-169 */
       controller_elect_leader(c, s, o);
       controller_shrink_isr(c, s, o);
@@ -838,7 +851,7 @@ static int in_model(const Cfg* c, const void* s) {
 /* bit mask of violated invariants among those requested */
 static unsigned violated(const Cfg* c, const void* s, unsigned want) {
   unsigned v = 0;
-  if (c->model >= M_TRUNCHW && c->model <= M_FIRSTTRY) {
+  if (IS_KAFKA(c->model)) {
     if ((want >> INV_WEAKISR) & 1) if (!isr_property(c, s, 0)) v |= 1u << INV_WEAKISR;
     if ((want >> INV_STRONGISR) & 1) if (!isr_property(c, s, 1)) v |= 1u << INV_STRONGISR;
     if ((want >> INV_LEADERINISR) & 1) if (!leader_in_isr(s)) v |= 1u << INV_LEADERINISR;
@@ -849,7 +862,7 @@ static unsigned violated(const Cfg* c, const void* s, unsigned want) {
 }
 static void init_state(const Cfg* c, void* s) {
   memset(s, 0, c->ssize);
-  if (c->model >= M_TRUNCHW && c->model <= M_FIRSTTRY) {      /* KafkaReplication.tla:109-120 */
+  if (IS_KAFKA(c->model)) {      /* KafkaReplication.tla:109-120 */
     KState* k = s;
     for (int r = 0; r < NMAX; ++r) { k->rs_epoch[r] = 0; k->rs_leader[r] = 0; }
     for (int r = 0; r < c->n; ++r) { k->rs_epoch[r] = -1; k->rs_leader[r] = NONE; }
@@ -1015,7 +1028,7 @@ int kso_run(int model, const int* params, int threads, uint64_t max_states, unsi
 /* symmetry != 0: SYMMETRY Permutations(Replicas) (Kafka family only) */
 int kso_run_sym(int model, const int* params, int threads, uint64_t max_states, unsigned inv_mask, kso_result* res,
                 uint8_t* dump, uint64_t dump_cap, int symmetry) {
-  if (symmetry && !(model >= M_TRUNCHW && model <= M_FIRSTTRY)) return -3;
+  if (symmetry && !IS_KAFKA(model)) return -3;
   Bfs* b = calloc(1, sizeof(Bfs));
   b->symmetry = symmetry;
   Cfg* c = &b->cfg;
@@ -1120,3 +1133,45 @@ int kso_run_sym(int model, const int* params, int threads, uint64_t max_states, 
 }
 
 size_t kso_state_size(int model) { return state_size(model); }
+
+/* ------------------------------------------------------------------------------------------
+ * single-state entry points (tests/: every step of an error trace printed by the product is
+ * re-checked here as a successor under THIS restatement of Next, not under the lowered code)
+ * ---------------------------------------------------------------------------------------- */
+static int fill_cfg(Cfg* c, int model, const int* params) {
+  memset(c, 0, sizeof(*c));
+  c->model = model;
+  c->ssize = state_size(model);
+  switch (model) {
+    case M_IDSEQ: c->E = params[0]; break;
+    case M_FRL: c->n = params[0]; c->L = params[1]; c->R = params[2]; break;
+    case M_ASYNCISR: c->n = params[0]; c->M = params[1]; c->V = params[2]; break;
+    default: c->n = params[0]; c->L = params[1]; c->R = params[2]; c->E = params[3]; break;
+  }
+  if (c->n > NMAX || c->L > LMAX || (model != M_IDSEQ && c->E > EMAX)) return -1;
+  return 0;
+}
+/* successors of *state (TLC multiplicity: duplicates kept) into out_buf; returns their number, < 0 on error */
+int kso_successors(int model, const int* params, const void* state, uint8_t* out_buf, int cap) {
+  Cfg c;
+  if (fill_cfg(&c, model, params)) return -1;
+  uint8_t* tmp = malloc((size_t)MAX_SUCC * c.ssize);
+  Out o = {tmp, 0, &c};
+  expand(&c, state, &o);
+  int n = o.n;
+  if (n > cap) { free(tmp); return -2; }
+  memcpy(out_buf, tmp, (size_t)n * c.ssize);
+  free(tmp);
+  return n;
+}
+int kso_init_state(int model, const int* params, void* out) {
+  Cfg c;
+  if (fill_cfg(&c, model, params)) return -1;
+  init_state(&c, out);
+  return 0;
+}
+unsigned kso_violated(int model, const int* params, const void* state, unsigned want) {
+  Cfg c;
+  if (fill_cfg(&c, model, params)) return 0;
+  return violated(&c, state, want);
+}

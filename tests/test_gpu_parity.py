@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 ALL_MODELS = ["idsequence", "frl_tiny", "frl_3x4x2", "frl_3x4x3", "kip320_n2", "trunchw_n2", "kip101_n2", "kip279_n2",
               "firsttry_n2", "kip320_small", "trunchw_small", "kip101_small", "kip279_small", "firsttry_small",
-              "asyncisr_v2", "asyncisr_small", "kip320sym_n2", "kip320sym_small", "minilock"]
+              "asyncisr_v2", "asyncisr_small", "kip320sym_n2", "kip320sym_small", "minilock", "kip320_with279_small"]
 DIGEST_MODELS = ["minilock", "idsequence", "frl_tiny", "kip320_n2", "trunchw_n2", "kip101_n2", "kip279_n2", "firsttry_n2",
                  "asyncisr_v2", "asyncisr_small"]
 
@@ -161,30 +161,61 @@ def test_probe_count_matches_generated(goldens):
 
 
 def _assert_trace_is_behaviour(name, trace, ck):
-    """Each step of the trace must be a successor of the previous state under the lowered Next,
-    checked with the host build of the same model header (g++ is available on the box)."""
-    import hashlib
-    hdr = os.path.join(ROOT, "build", "models", name, "model.h")
-    tag = hashlib.sha256(open(hdr, "rb").read()).hexdigest()[:12]
-    out = os.path.join(ROOT, "build", "hosttest")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, f"succ_{name}_{tag}.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f'-DKMC_MODEL_HEADER="{hdr}"',
-                               os.path.join(ROOT, "tests", "support", "host_succ.cpp"), "-o", so])
-    lib = ctypes.CDLL(so)
-    lib.kmc_host_is_successor.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    lib.kmc_host_is_init.argtypes = [ctypes.c_void_p]
-    w0 = np.array(trace[0]["words"], dtype=np.uint64)
-    assert lib.kmc_host_is_init(w0.ctypes.data) == 1
-    for a, b in zip(trace, trace[1:]):
-        wa = np.array(a["words"], dtype=np.uint64)
-        wb = np.array(b["words"], dtype=np.uint64)
-        act = lib.kmc_host_is_successor(wa.ctypes.data, wb.ctypes.data)
-        assert act >= 0, "trace step is not a successor"
-    wl = np.array(trace[-1]["words"], dtype=np.uint64)
-    lib.kmc_host_first_violated.argtypes = [ctypes.c_void_p]
-    assert lib.kmc_host_first_violated(wl.ctypes.data) >= 0
+    """Every step of the error trace is re-checked against ORACLE B (the hand-written C restatement of the spec,
+    independent of the front end and of the lowering): the first state is its Init, each state is among the
+    successors its Next enumerates for the previous one, and the last state violates the reported invariant
+    there too.  (Round 1 validated the steps with the lowered header itself, which a lowering bug would pass.)"""
+    import json
+    import kso
+    reg = json.load(open(os.path.join(ROOT, "models", "MODELS.json")))[name]
+    model, params = reg["kso"]
+    states = [ck.decoder.decode(t["words"]) for t in trace]
+    replicas = sorted(states[0]["replicaLog"].domain(), key=str)
+    recs = [kso.kstate_from_tla(st, replicas) for st in states]
+    assert recs[0] == kso.init_state(model, params), "trace does not start in the oracle's initial state"
+    for i, (a, b) in enumerate(zip(recs, recs[1:])):
+        assert b in kso.successors(model, params, a), f"trace step {i + 1} -> {i + 2} is not a successor under Oracle B"
+    assert kso.violated(model, params, recs[-1], ck.meta["invariants"]), "last trace state violates nothing under Oracle B"
+    for a in recs[:-1]:
+        assert not kso.violated(model, params, a, ck.meta["invariants"]), "an earlier trace state already violates"
+
+
+@pytest.mark.parametrize("name", ["trunchw_small", "kip101_small", "kip279_small", "firsttry_small", "kip320_with279_small"])
+def test_error_traces_are_behaviours_under_oracle_b(name, goldens):
+    """Default run (stop at the first violation) of every protocol variant the reference says is broken:
+    shortest counterexample, each step validated by Oracle B."""
+    g = goldens[name]
+    first = min(l for l in g["first_violation_level"].values() if l)
+    with checker(name) as ck:
+        r = ck.run()
+        assert not r.complete and r.violation["kind"] == "invariant" and r.violation["level"] == first
+        assert len(r.trace) == first and r.trace[0]["action"] is None
+        assert all(t["action"] is not None for t in r.trace[1:])
+        _assert_trace_is_behaviour(name, r.trace, ck)
+
+
+def test_kip320_needs_its_epoch_check_as_the_reference_says(goldens):
+    """Kip320.tla:126-133: replacing FencedBecomeFollowerAndTruncate with BecomeFollowerTruncateKip279 breaks
+    StrongIsr; with the action as written (kip320_small) all invariants hold."""
+    g = goldens["kip320_with279_small"]
+    assert g["first_violation_level"]["StrongIsr"] is not None
+    with checker("kip320_with279_small", cont=True) as ck:
+        r = ck.run()
+    assert (r.distinct, r.generated, r.depth, r.levels) == (g["distinct"], g["generated"], g["depth"], g["levels"])
+    assert r.violation is not None and r.violation["level"] == g["first_violation_level"]["StrongIsr"]
+    with checker("kip320_small", cont=True) as ck:
+        assert ck.run().violation is None
+
+
+def test_config5_asyncisr_deep_matches_oracle_b_golden(goldens):
+    """BASELINE config #5 (AsyncIsr, deep bounds): 294 M states, exact 104-bit keys, against the Oracle B golden."""
+    g = goldens["asyncisr_deep"]
+    with checker("asyncisr_deep", table_log2=30, max_states=300_000_000) as ck:
+        r = ck.run()
+        assert ck.info.exact == 1
+    assert r.complete and r.violation is None
+    assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
+        g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
 
 
 @pytest.mark.parametrize("name,opts", [("kip320_3x4_r4e2", {"table_log2": 26, "max_states": 20_000_000}),

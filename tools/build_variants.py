@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from kafka_specification_b200 import build as B  # noqa: E402
 
-LOWER = {"g200": {"guard_lines": 200}, "g800": {"guard_lines": 800}, "g1600s32": {"guard_lines": 1600, "max_group_sites": 32}}
+LOWER = {"g200": {"guard_lines": 200}, "g3000": {"guard_lines": 3000}, "g800": {"guard_lines": 800}, "g1600s32": {"guard_lines": 1600, "max_group_sites": 32}}
 
 
 def main():
