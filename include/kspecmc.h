@@ -171,6 +171,21 @@ int kmc_shard_seed_p2p(kmc_ctx* ctx);
 int kmc_shard_expand_p2p(kmc_ctx* ctx, uint64_t first, uint64_t count);
 int kmc_shard_insert_p2p(kmc_ctx* ctx);
 
+/* ---- the same with DEVICE-SIDE cross-rank synchronisation (no NCCL collective, no host wait inside a level) ----
+ * A sync page in front of every inbox holds per-source "ready" and per-destination "done" round counters and a
+ * level board; peers push into it over NVLink, its owner polls it locally from tiny wait kernels on the stream.
+ * kmc_shard_round_p2p   one expand (or, seed != 0, initial states) -> exchange -> insert round; every rank calls it
+ *                       the same number of times per level (count = 0 on ranks without work)
+ * kmc_shard_level_sync  invariants + publish this rank's level summary to all ranks + wait for all summaries; the ONE
+ *                       host synchronisation of a level.  board receives world x 8 words per rank:
+ *                       {level id, new states, violations, store tail, generated, fail, deadlocks, -}
+ * kmc_shard_inbox_ptr / kmc_shard_open_peers_direct: peers inside one process (one ctx per GPU, host threads):
+ *                       direct device pointers + cudaDeviceEnablePeerAccess instead of CUDA IPC handles.           */
+int kmc_shard_round_p2p(kmc_ctx* ctx, uint64_t first, uint64_t count, int seed);
+int kmc_shard_level_sync(kmc_ctx* ctx, uint64_t* board /* world x 8 */);
+int kmc_shard_inbox_ptr(kmc_ctx* ctx, void** out);
+int kmc_shard_open_peers_direct(kmc_ctx* ctx, void* const* inboxes, const int* devices, uint32_t world);
+
 #ifdef __cplusplus
 }
 #endif

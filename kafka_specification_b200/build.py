@@ -81,7 +81,9 @@ VARIANTS = {
     "": ["-DKMC_NO_ONE_PHASE"],
     "1p": ["-DKMC_ONE_PHASE"],
     "b512": ["-DKMC_NO_ONE_PHASE", "-DEXPAND_BLOCK_THREADS=512", "-DEXPAND_CTAS_PER_SM=2"],    # two 512-thread CTAs per SM
-    "bs4": ["-DKMC_NO_ONE_PHASE", "-DKMC_BUCKET_SLOTS=4"],                                   # 64-byte buckets of 16-byte keys
+    "bs4": ["-DKMC_NO_ONE_PHASE", "-DKMC_BUCKET_SLOTS=4"],
+    "b768": ["-DKMC_NO_ONE_PHASE", "-DEXPAND_BLOCK_THREADS=768"],      # 24 warps: leaves registers for K2 blocks (overlap)
+    "b512x1": ["-DKMC_NO_ONE_PHASE", "-DEXPAND_BLOCK_THREADS=512"],                                   # 64-byte buckets of 16-byte keys
 }
 
 

@@ -40,6 +40,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -191,6 +192,7 @@ struct Params {
   uint32_t check_deadlock;
   uint32_t count_actions;
   uint32_t prefetch;        // K1 issues an L2 prefetch of every candidate's first bucket (see flush_stage)
+  uint32_t cand_slot;       // single rank: which half of the candidate buffer (and which counter) this launch uses
   // fused exchange (world > 1, after kmc_shard_open_peers): every rank's inbox, mapped into this
   // process through CUDA IPC.  An inbox is two buffers (double buffering); a buffer is an 8-word
   // header (rows sent by each source rank) followed by world regions of region_rows rows.
@@ -201,6 +203,14 @@ struct Params {
 };
 
 static constexpr int INBOX_HEADER = 8;
+// Sync page in front of every rank's inbox (same allocation, so peers map it with the inbox).  Peers PUSH into it
+// (posted NVLink stores) and its owner polls it locally:
+//   ready[src]   round number src has finished storing rows (and their counts) for, into this rank's inbox
+//   done[dst]    round number dst has finished inserting from ITS inbox (so its buffer of that round may be reused)
+//   board[r][8]  rank r's level summary {level id, new states, violations, store tail, generated, fail, deadlocks, -}
+// All counters are monotonic over the life of the context (never reset), so no reset can race with a peer.
+static constexpr int SYNC_WORDS = 256;
+static constexpr int SYNC_READY = 0, SYNC_DONE = 8, SYNC_BOARD = 16, BOARD_WORDS = 8;
 
 __device__ __forceinline__ unsigned lane_id() {
   unsigned r;
@@ -454,7 +464,7 @@ __device__ __forceinline__ void flush_stage(const Params& p, uint32_t wbuf, uint
   unsigned lane = lane_id();
   if (p.world == 1) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&p.ctr->cand_count[0], (unsigned long long)n);
+    if (lane == 0) base = atomicAdd(&p.ctr->cand_count[p.cand_slot], (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + n > p.region_rows) {
       failed = KMC_FAIL_CAND_FULL;
@@ -634,13 +644,21 @@ struct SiteGroupRunner {
         nsucc[j] += (unsigned)__popcll(masks[j]);
       }
     }
+    // a state enables ~0.6 sites of a group on average: three predicated steps (no loop control, no
+    // reconvergence stack) cover nearly every mask; the loop behind them is the rare tail
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       uint64_t m = masks[j];
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        if (m) {
+          atoms_add(cnt + (__ffsll((long long)m) - 1) * 4, 1u);
+          m &= m - 1;
+        }
+      }
       while (m) {
-        const int k = __ffsll((long long)m) - 1;
+        atoms_add(cnt + (__ffsll((long long)m) - 1) * 4, 1u);
         m &= m - 1;
-        atoms_add(cnt + k * 4, 1u);
       }
     }
     __syncthreads();                                   // totals complete; B of the previous group finished
@@ -687,17 +705,22 @@ struct SiteGroupRunner {
       if (in1) { k_lo = min(k_lo, 2 * (__ffs(in1) - 1) + 1); k_hi = max(k_hi, 2 * (31 - __clz(in1)) + 2); }
       if (r0) __syncthreads();                         // later rounds: the previous round's list is consumed
       // ---- A2: every thread scatters its own pairs: slot = cursor[site]++ inside the site's segment
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        uint64_t m = masks[j];
-        while (m) {
-          const int k = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          if (k < k_lo || k >= k_hi) continue;         // empty sites in between have no pairs
+      auto scatter_one = [&](uint64_t& m, int j) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (k >= k_lo && k < k_hi) {                   // (a later round takes the sites outside)
           const unsigned st = lds32(c.seg + k * 4);
           const unsigned pos = (st - r0) * 32 + atoms_add(c.cur + k * 4, 1u);
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(c.list + pos * 2), "h"((unsigned short)((unsigned)j * EXPAND_BLOCK + threadIdx.x)) : "memory");
         }
+      };
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        uint64_t m = masks[j];
+#pragma unroll
+        for (int it = 0; it < 3; ++it)
+          if (m) scatter_one(m, j);
+        while (m) scatter_one(m, j);
       }
       __syncthreads();                                 // list complete (also orders the clearing of the other totals buffer)
       if (threadIdx.x < MAX_GROUP_SITES) sts32(c.cur + threadIdx.x * 4, 0u);   // cursors ready for the next scatter
@@ -835,7 +858,7 @@ struct GroupRunner {
           State s;
           load_state(s, p.store + (first + i) * W);
           CandSink sink{(first + i) | ((uint64_t)p.rank << 40), wbuf, wcnt, p.count_actions ? p.ctr->action_counts : nullptr, 0, 0,
-                        p.world == 1 ? p.cand : nullptr, &p.ctr->cand_count[0], p.region_rows};
+                        p.world == 1 ? p.cand : nullptr, &p.ctr->cand_count[p.cand_slot], p.region_rows};
           M::expand_group(M::GroupTag<G>{}, s, sink);
           nsucc[j] += (unsigned)sink.n;
           failed |= sink.failed;
@@ -946,10 +969,81 @@ __global__ void __launch_bounds__(256) k_insert(Params p, const uint64_t* rows, 
   }
 }
 
-// Fused exchange, step 2: tell every owner how many rows this rank stored in its inbox region.
-__global__ void k_publish_counts(Params p) {
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t* sync_page(const Params& p, uint32_t r) { return p.peer_inbox[r] - SYNC_WORDS; }
+
+// Fused exchange, step 2: tell every owner how many rows this rank stored in its inbox region and (round > 0)
+// raise this rank's ready flag there.  The expand kernel that stored the rows is complete (stream order); the
+// system-scope fence + release store order its peer writes before the flag.
+__global__ void k_publish_counts(Params p, uint64_t round) {
   unsigned d = threadIdx.x;
-  if (d < p.world) p.peer_inbox[d][(uint64_t)p.inbox_buf * p.inbox_stride + p.rank] = p.ctr->cand_count[d];
+  if (d < p.world) {
+    p.peer_inbox[d][(uint64_t)p.inbox_buf * p.inbox_stride + p.rank] = p.ctr->cand_count[d];
+    if (round) {
+      __threadfence_system();
+      st_release_sys(sync_page(p, d) + SYNC_READY + p.rank, round);
+    }
+  }
+}
+
+// Device-side wait (one warp): lane i spins until flags[i] >= value.  The flags live in this rank's own memory
+// (peers push), so the polling never crosses NVLink.
+__global__ void k_wait_flags(const uint64_t* flags, unsigned n, uint64_t value) {
+  unsigned i = threadIdx.x;
+  if (i < n) {
+    unsigned ns = 32;
+    while (ld_acquire_sys(flags + i) < value) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+    }
+  }
+}
+
+// after the insert of a round: every source may now reuse this rank's inbox buffer of that round
+__global__ void k_publish_done(Params p, uint64_t round) {
+  unsigned s = threadIdx.x;
+  if (s < p.world) {
+    __threadfence_system();
+    st_release_sys(sync_page(p, s) + SYNC_DONE + p.rank, round);
+  }
+}
+
+// Level end: this rank's summary goes to every rank's board (peer stores), ...
+__global__ void k_publish_level(Params p, uint64_t level_id, uint64_t prev_tail) {
+  unsigned d = threadIdx.x;
+  if (d < p.world) {
+    uint64_t* e = sync_page(p, d) + SYNC_BOARD + p.rank * BOARD_WORDS;
+    const unsigned long long tail = p.ctr->store_tail;
+    e[1] = tail - prev_tail;
+    e[2] = p.ctr->viol_count;
+    e[3] = tail;
+    e[4] = p.ctr->generated;
+    e[5] = p.ctr->fail;
+    e[6] = p.ctr->deadlocks;
+    __threadfence_system();
+    st_release_sys(e, level_id);
+  }
+}
+// ... and once every rank's entry of this level has arrived the whole board is copied to pinned host memory:
+// the host's single synchronisation per level is the stream sync after this kernel.
+__global__ void k_gather_level(Params p, uint64_t level_id, uint64_t* host_out) {
+  unsigned r = threadIdx.x;
+  const uint64_t* board = sync_page(p, p.rank) + SYNC_BOARD;
+  if (r < p.world) {
+    unsigned ns = 32;
+    while (ld_acquire_sys(board + r * BOARD_WORDS) < level_id) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+    }
+    for (int k = 0; k < BOARD_WORDS; ++k) host_out[r * BOARD_WORDS + k] = board[r * BOARD_WORDS + k];
+  }
 }
 
 // Fused exchange, step 3 (after a cross-rank barrier): insert the rows of all source regions of
@@ -1057,6 +1151,10 @@ struct Engine {
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
   uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
+  bool overlap = false;             // single rank: K2 of chunk i runs on a second stream while K1 expands chunk i+1
+                                    // (K1 is issue-bound, K2 waits on random DRAM sectors: they use different units)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_exp[2] = {nullptr, nullptr}, ev_ins[2] = {nullptr, nullptr};
   bool prefetch = false;            // K1 prefetches candidate buckets into L2 (pair with a small chunk_states)
   uint64_t chunk_states_opt = 0;    // frontier states per K1/K2 launch pair (0: as many as the candidate buffer allows)
   bool one_phase = false;           // comparison only: the round-1 one-phase K1 (needs a -DKMC_ONE_PHASE build)
@@ -1069,10 +1167,15 @@ struct Engine {
   uint64_t region_rows = 0;
   uint64_t* recv = nullptr;
   uint64_t recv_rows = 0;
-  uint64_t* inbox = nullptr;          // fused exchange: 2 x (header + world regions), shared through CUDA IPC
+  uint64_t* inbox_alloc = nullptr;    // sync page + 2 inbox buffers, shared through CUDA IPC
+  uint64_t* board_host = nullptr;     // pinned: the level board as gathered by k_gather_level
+  uint64_t round = 0, level_id = 0;   // monotonic over the life of the context (see SYNC_WORDS)
+  uint64_t prev_tail = 0;
+  uint64_t* inbox = nullptr;          // fused exchange: 2 x (header + world regions)
   uint64_t inbox_stride = 0;
   uint64_t* peer_inbox[MAX_WORLD] = {};
   bool peers_open = false;
+  bool peers_direct = false;          // peer pointers given directly (same process, cudaDeviceEnablePeerAccess)
   uint32_t inbox_buf = 0;
   uint64_t exchanged_rows = 0;
   DevCounters* ctr = nullptr;
@@ -1117,6 +1220,7 @@ struct Engine {
     p.check_deadlock = check_deadlock ? 1 : 0;
     p.count_actions = count_actions ? 1 : 0;
     p.prefetch = prefetch ? 1 : 0;
+    p.cand_slot = 0;
     for (int r = 0; r < MAX_WORLD; ++r) p.peer_inbox[r] = peer_inbox[r];
     p.inbox_stride = inbox_stride;
     p.p2p = 0;
@@ -1127,6 +1231,10 @@ struct Engine {
 
 struct kmcm_ctx {
   Engine e;
+  // option "gpus": N > 1 -- this context drives N GPUs of the process: one sub-context (rank) per device, peers
+  // mapped directly (cudaDeviceEnablePeerAccess), one host thread per rank inside kmcm_run.  `e` then only
+  // holds the aggregated results.
+  std::vector<kmcm_ctx*> ranks;
 };
 
 #define CK(call)                                                                                         \
@@ -1182,17 +1290,18 @@ static cudaEvent_t get_event(Engine& E) {
 struct TimedLaunch {
   Engine& E;
   int kind;
+  cudaStream_t on;
   cudaEvent_t a = nullptr, b = nullptr;
-  TimedLaunch(Engine& e, int k) : E(e), kind(k) {
+  TimedLaunch(Engine& e, int k, cudaStream_t s = nullptr) : E(e), kind(k), on(s ? s : e.stream) {
     if (E.timing) {
       a = get_event(E);
       b = get_event(E);
-      cudaEventRecord(a, E.stream);
+      cudaEventRecord(a, on);
     }
   }
   ~TimedLaunch() {
     if (E.timing) {
-      cudaEventRecord(b, E.stream);
+      cudaEventRecord(b, on);
       E.launches.push_back({kind, a, b});
     }
   }
@@ -1246,7 +1355,8 @@ static int engine_alloc(Engine& E) {
     E.max_states = std::max<uint64_t>(1024, std::min<uint64_t>(E.table_slots / 2, room));
   }
   uint64_t rows_total = E.cand_bytes / (ROW * 8);
-  E.region_rows = rows_total / E.world;
+  if (E.world > 1) E.overlap = false;                    // (the fused exchange double-buffers on its own)
+  E.region_rows = rows_total / (E.overlap ? 2 : E.world);
   if (E.region_rows < (uint64_t)M::MAX_FANOUT) E.region_rows = M::MAX_FANOUT;
   // A chunk of frontier states is sized for `fanout_bound` successors per state on average *per owner region*.
   // MAX_FANOUT (emit sites in expand) is a safe but very loose bound -- reachable states enable a small
@@ -1256,16 +1366,26 @@ static int engine_alloc(Engine& E) {
   E.chunk_states = std::max<uint64_t>(1, E.region_rows / E.fanout_bound);
   if (E.chunk_states_opt) E.chunk_states = std::min<uint64_t>(E.chunk_states, E.chunk_states_opt);
   if (E.own_stream) CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+  if (E.overlap) {
+    CK(cudaStreamCreateWithFlags(&E.stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&E.ev_exp[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&E.ev_ins[i], cudaEventDisableTiming));
+    }
+  }
   CK(cudaMalloc(&E.table, E.table_slots * SLOT_BYTES));
   CK(cudaMalloc(&E.store, E.max_states * W * 8));
   CK(cudaMalloc(&E.parent, E.max_states * 8));
-  CK(cudaMalloc(&E.cand, E.region_rows * E.world * ROW * 8));
+  CK(cudaMalloc(&E.cand, E.region_rows * (E.overlap ? 2 : E.world) * ROW * 8));
   if (E.world > 1) {
     E.recv_rows = E.region_rows * E.world;
     CK(cudaMalloc(&E.recv, E.recv_rows * ROW * 8));
     E.inbox_stride = INBOX_HEADER + E.region_rows * E.world * ROW;
-    CK(cudaMalloc(&E.inbox, 2 * E.inbox_stride * 8));
-    CK(cudaMemset(E.inbox, 0, 2 * E.inbox_stride * 8));
+    CK(cudaMalloc(&E.inbox_alloc, (SYNC_WORDS + 2 * E.inbox_stride) * 8));
+    CK(cudaMemset(E.inbox_alloc, 0, (SYNC_WORDS + 2 * E.inbox_stride) * 8));
+    E.inbox = E.inbox_alloc + SYNC_WORDS;
+    CK(cudaHostAlloc(&E.board_host, MAX_WORLD * BOARD_WORDS * 8, cudaHostAllocMapped));
+    memset(E.board_host, 0, MAX_WORLD * BOARD_WORDS * 8);
   }
   // the expand kernel keeps its state tile, the successor stage and the pair list in > 48 KB of dynamic shared memory
   CK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPAND_SMEM_BYTES));
@@ -1349,11 +1469,11 @@ static int seed_init(Engine& E) {
 }
 
 static int launch_insert(Engine& E, const uint64_t* rows, const unsigned long long* n_dev, uint64_t n_fixed,
-                         uint64_t n_bound) {
+                         uint64_t n_bound, cudaStream_t on = nullptr) {
   Params p = E.params();
   {
-    TimedLaunch t(E, 1);
-    k_insert<<<grid_for(E, n_bound, 256, 8), 256, 0, E.stream>>>(p, rows, n_dev, n_fixed);
+    TimedLaunch t(E, 1, on);
+    k_insert<<<grid_for(E, n_bound, 256, 8), 256, 0, on ? on : E.stream>>>(p, rows, n_dev, n_fixed);
   }
   CK(cudaGetLastError());
   return KMC_OK;
@@ -1368,9 +1488,11 @@ static int launch_invariants(Engine& E, uint64_t first, uint64_t count_bound) {
   return KMC_OK;
 }
 
-static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool p2p = false) {
+static int launch_expand(Engine& E, uint64_t first, uint64_t count, bool p2p = false, uint32_t slot = 0) {
   Params p = E.params();
   p.p2p = p2p ? 1 : 0;
+  p.cand_slot = slot;
+  p.cand = E.cand + (uint64_t)slot * E.region_rows * ROW;
   if (count == 0) return KMC_OK;
   TimedLaunch t(E, 0);
 #ifdef KMC_ONE_PHASE
@@ -1483,11 +1605,29 @@ static int engine_run(Engine& E) {
   }
   while (!err && !stopped && level_end > level_first) {
     E.widths.push_back(level_end - level_first);
-    for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
-      uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
-      if ((rc = reset_cand(E))) return rc;
-      if ((rc = launch_expand(E, off, cnt))) return rc;
-      if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
+    if (E.overlap) {
+      // K1 of chunk i+1 (stream) overlaps K2 of chunk i (stream2); the two halves of the candidate buffer alternate
+      uint32_t slot = 0;
+      for (uint64_t off = level_first; off < level_end; off += E.chunk_states, slot ^= 1) {
+        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+        CK(cudaStreamWaitEvent(E.stream, E.ev_ins[slot], 0));            // the K2 that read this half has finished
+        CK(cudaMemsetAsync(&E.ctr->cand_count[slot], 0, sizeof(unsigned long long), E.stream));
+        if ((rc = launch_expand(E, off, cnt, false, slot))) return rc;
+        CK(cudaEventRecord(E.ev_exp[slot], E.stream));
+        CK(cudaStreamWaitEvent(E.stream2, E.ev_exp[slot], 0));
+        if ((rc = launch_insert(E, E.cand + (uint64_t)slot * E.region_rows * ROW, &E.ctr->cand_count[slot], 0,
+                                cnt * (uint64_t)E.fanout_bound, E.stream2))) return rc;
+        CK(cudaEventRecord(E.ev_ins[slot], E.stream2));
+      }
+      CK(cudaStreamWaitEvent(E.stream, E.ev_ins[0], 0));
+      CK(cudaStreamWaitEvent(E.stream, E.ev_ins[1], 0));
+    } else {
+      for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
+        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+        if ((rc = reset_cand(E))) return rc;
+        if ((rc = launch_expand(E, off, cnt))) return rc;
+        if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
+      }
     }
     if ((rc = launch_invariants(E, level_end, (level_end - level_first) * 2))) return rc;
     if ((rc = read_counters(E, &h))) return rc;
@@ -1548,6 +1688,9 @@ static int engine_run(Engine& E) {
 // ----------------------------------------------------------------------------------------
 // exported per-model ABI (the dispatcher libkspecmc.so forwards kmc_* to these)
 // ----------------------------------------------------------------------------------------
+static int multi_create(kmcm_ctx* c, const char* options_json, int gpus);
+static int multi_run(kmcm_ctx* c);
+
 #define E (c->e)
 extern "C" {
 
@@ -1570,6 +1713,7 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_num(options_json, "l2_fetch", &d)) E.l2_fetch = (int)d;
   if (json_bool(options_json, "one_phase", &b)) E.one_phase = b;
   if (json_bool(options_json, "prefetch", &b)) E.prefetch = b;
+  if (json_bool(options_json, "overlap", &b)) E.overlap = b;
   if (json_num(options_json, "chunk_states", &d)) E.chunk_states_opt = (uint64_t)d;
   if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
@@ -1582,6 +1726,10 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
     delete c;
     return KMC_E_BADARG;
   }
+  if (json_num(options_json, "gpus", &d) && d > 1) {
+    *out = c;
+    return multi_create(c, options_json, (int)d);
+  }
   int rc = engine_alloc(E);
   *out = c;   // returned even on failure so that the caller can read the error text
   if (rc == KMC_OK) rc = engine_reset(E);
@@ -1590,6 +1738,11 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
 
 void kmcm_destroy(kmcm_ctx* c) {
   if (!c) return;
+  if (!c->ranks.empty()) {
+    for (kmcm_ctx* r : c->ranks) kmcm_destroy(r);
+    delete c;
+    return;
+  }
   cudaSetDevice(E.device);
   cudaFree(E.table);
   cudaFree(E.store);
@@ -1598,14 +1751,20 @@ void kmcm_destroy(kmcm_ctx* c) {
   cudaFree(E.recv);
   if (E.peers_open)
     for (uint32_t r = 0; r < E.world; ++r)
-      if (r != E.rank && E.peer_inbox[r]) cudaIpcCloseMemHandle(E.peer_inbox[r]);
-  cudaFree(E.inbox);
+      if (r != E.rank && E.peer_inbox[r] && !E.peers_direct) cudaIpcCloseMemHandle(E.peer_inbox[r] - SYNC_WORDS);
+  cudaFree(E.inbox_alloc);
+  if (E.board_host) cudaFreeHost(E.board_host);
   cudaFree(E.ctr);
   cudaFree(E.viol_ring);
   for (cudaEvent_t ev : E.event_pool) cudaEventDestroy(ev);
   if (E.ev_begin) cudaEventDestroy(E.ev_begin);
   if (E.ev_end) cudaEventDestroy(E.ev_end);
   if (E.stream && E.own_stream) cudaStreamDestroy(E.stream);
+  if (E.stream2) cudaStreamDestroy(E.stream2);
+  for (int i = 0; i < 2; ++i) {
+    if (E.ev_exp[i]) cudaEventDestroy(E.ev_exp[i]);
+    if (E.ev_ins[i]) cudaEventDestroy(E.ev_ins[i]);
+  }
   delete c;
 }
 
@@ -1627,6 +1786,7 @@ int kmcm_model_info(const kmcm_ctx*, kmc_model_info_t* out) {
 
 int kmcm_run(kmcm_ctx* c) {
   if (!c) return KMC_E_BADARG;
+  if (!c->ranks.empty()) return multi_run(c);
   return engine_run(E);
 }
 
@@ -1680,6 +1840,7 @@ int kmcm_violation_record(const kmcm_ctx* c, uint64_t* words, size_t cap_words, 
 int kmcm_copy_parents(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64_t* buf) {
   kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
   if (!c || !buf) return KMC_E_BADARG;
+  if (!c->ranks.empty()) return KMC_E_STATE;      // per-rank stores: address a rank's own context
   if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaSetDevice(E.device));
   CK(cudaMemcpy(buf, E.parent + first, count * 8, cudaMemcpyDeviceToHost));
@@ -1689,6 +1850,7 @@ int kmcm_copy_parents(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64
 int kmcm_copy_states(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64_t* buf) {
   kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
   if (!c || !buf) return KMC_E_BADARG;
+  if (!c->ranks.empty()) return KMC_E_STATE;
   if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaSetDevice(E.device));
   CK(cudaMemcpy(buf, E.store + first * W, count * W * 8, cudaMemcpyDeviceToHost));
@@ -1847,7 +2009,7 @@ int kmcm_shard_ipc_handle(kmcm_ctx* c, void* out64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
   CK(cudaSetDevice(E.device));
-  CK(cudaIpcGetMemHandle(&h, E.inbox));
+  CK(cudaIpcGetMemHandle(&h, E.inbox_alloc));
   memcpy(out64, &h, 64);
   return KMC_OK;
 }
@@ -1864,7 +2026,7 @@ int kmcm_shard_open_peers(kmcm_ctx* c, const void* handles, uint32_t world) {
     memcpy(&h, (const char*)handles + 64 * r, 64);
     void* ptr = nullptr;
     CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    E.peer_inbox[r] = (uint64_t*)ptr;
+    E.peer_inbox[r] = (uint64_t*)ptr + SYNC_WORDS;
   }
   E.peers_open = true;
   return KMC_OK;
@@ -1882,14 +2044,14 @@ int kmcm_shard_expand_p2p(kmcm_ctx* c, uint64_t first, uint64_t count) {
   p.p2p = 1;
   {
     TimedLaunch t(E, 2);
-    k_publish_counts<<<1, 32, 0, E.stream>>>(p);
+    k_publish_counts<<<1, 32, 0, E.stream>>>(p, 0);
   }
   CK(cudaGetLastError());
   return KMC_OK;
 }
 
 // seed: the initial states go through the same inbox path (rank 0 contributes them)
-int kmcm_shard_seed_p2p(kmcm_ctx* c) {
+static int seed_p2p(kmcm_ctx* c, bool publish) {
   if (!c || !E.peers_open) return KMC_E_STATE;
   CK(cudaSetDevice(E.device));
   unsigned long long counts[MAX_WORLD] = {0};
@@ -1911,13 +2073,16 @@ int kmcm_shard_seed_p2p(kmcm_ctx* c) {
     CK(cudaMemcpyAsync(&E.ctr->generated, &gen, sizeof(gen), cudaMemcpyHostToDevice, E.stream));
   }
   CK(cudaMemcpyAsync(E.ctr, counts, sizeof(counts), cudaMemcpyHostToDevice, E.stream));
-  Params p = E.params();
-  p.p2p = 1;
-  k_publish_counts<<<1, 32, 0, E.stream>>>(p);
-  CK(cudaGetLastError());
+  if (publish) {
+    Params p = E.params();
+    p.p2p = 1;
+    k_publish_counts<<<1, 32, 0, E.stream>>>(p, 0);
+    CK(cudaGetLastError());
+  }
   CK(cudaStreamSynchronize(E.stream));
   return KMC_OK;
 }
+int kmcm_shard_seed_p2p(kmcm_ctx* c) { return seed_p2p(c, true); }
 
 // insert everything the peers stored into the current inbox buffer, then switch buffers.
 // The caller must have put a cross-rank barrier on the stream between expand_p2p and this call.
@@ -1933,10 +2098,118 @@ int kmcm_shard_insert_p2p(kmcm_ctx* c) {
   return KMC_OK;
 }
 
+// One expand -> exchange -> insert round with device-side cross-rank synchronisation (no NCCL, no host wait):
+//   wait until every destination has consumed the buffer this round reuses (done >= round - 2)
+//   expand (or, seed != 0, store the initial states) straight into the owners' inboxes; publish counts + ready
+//   wait until every source is ready for this round; insert from the own inbox; publish done
+// Every rank must call it the same number of times (count = 0 on ranks without work).
+int kmcm_shard_round_p2p(kmcm_ctx* c, uint64_t first, uint64_t count, int seed) {
+  if (!c || !E.peers_open) return KMC_E_STATE;
+  if (count > E.chunk_states) return KMC_E_BADARG;
+  CK(cudaSetDevice(E.device));
+  const uint64_t round = ++E.round;
+  E.inbox_buf = (uint32_t)(round & 1);
+  int rc;
+  if (round > 2) k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_DONE, E.world, round - 2);
+  if (seed) {
+    if ((rc = seed_p2p(c, false))) return rc;
+  } else {
+    if ((rc = reset_cand(E))) return rc;
+    if ((rc = launch_expand(E, first, count, true))) return rc;
+  }
+  Params p = E.params();
+  p.p2p = 1;
+  k_publish_counts<<<1, 32, 0, E.stream>>>(p, round);
+  k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_READY, E.world, round);
+  {
+    TimedLaunch t(E, 1);
+    k_insert_inbox<<<E.sms * 8, 256, 0, E.stream>>>(p);
+  }
+  k_publish_done<<<1, 32, 0, E.stream>>>(p, round);
+  CK(cudaGetLastError());
+  return KMC_OK;
+}
+
+// Level end on all ranks at once: invariants on this rank's new states, publish the summary to every board, wait
+// for all summaries, copy the board to pinned host memory, ONE stream synchronisation.  board_out receives
+// world x 8 words: {level id, new states, violations, store tail, generated, fail, deadlocks, -} per rank.
+int kmcm_shard_level_sync(kmcm_ctx* c, uint64_t* board_out) {
+  if (!c || !E.peers_open || !board_out) return KMC_E_STATE;
+  CK(cudaSetDevice(E.device));
+  int rc = launch_invariants(E, E.level_first + E.level_count, std::max<uint64_t>(E.level_count * 2, 1024));
+  if (rc) return rc;
+  const uint64_t level_id = ++E.level_id;
+  Params p = E.params();
+  k_publish_level<<<1, 32, 0, E.stream>>>(p, level_id, E.level_first + E.level_count);
+  uint64_t* dev_view = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&dev_view, E.board_host, 0));
+  k_gather_level<<<1, 32, 0, E.stream>>>(p, level_id, dev_view);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(E.stream));
+  memcpy(board_out, E.board_host, (size_t)E.world * BOARD_WORDS * 8);
+  const uint64_t* mine = E.board_host + (size_t)E.rank * BOARD_WORDS;
+  const uint64_t prev_end = E.level_first + E.level_count;
+  E.level_first = prev_end;
+  E.level_count = mine[1];
+  E.shard_levels++;
+  {
+    std::lock_guard<std::mutex> g(E.mu);
+    E.stats.distinct = mine[3];
+    E.stats.generated = mine[4];
+    E.stats.deadlocks = mine[6];
+    E.stats.table_slots = E.table_slots;
+    E.stats.slot_bytes = SLOT_BYTES;
+    E.stats.max_states = E.max_states;
+    if (E.level_count) E.widths.push_back(E.level_count);
+    E.stats.levels = E.stats.depth = E.widths.size();
+  }
+  if (mine[2] && E.viol.kind == KMC_RESULT_OK) {
+    DevCounters h;
+    if ((rc = read_counters(E, &h))) return rc;
+    build_trace(E, h, E.shard_levels - 1);
+  }
+  return fail_to_error(mine[5]);
+}
+
+// same-process peers (one context per GPU in one process): direct pointers instead of CUDA IPC handles.
+// inboxes[r] = the value kmcm_shard_inbox_ptr returned for rank r's context.
+int kmcm_shard_inbox_ptr(kmcm_ctx* c, void** out) {
+  if (!c || !out || !E.inbox_alloc) return KMC_E_BADARG;
+  *out = E.inbox_alloc;
+  return KMC_OK;
+}
+int kmcm_shard_open_peers_direct(kmcm_ctx* c, void* const* inboxes, const int* devices, uint32_t world) {
+  if (!c || !inboxes || !devices || world != E.world || !E.inbox_alloc) return KMC_E_BADARG;
+  CK(cudaSetDevice(E.device));
+  for (uint32_t r = 0; r < world; ++r) {
+    if (r != E.rank) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        E.last_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+        return KMC_E_CUDA;
+      }
+      cudaGetLastError();
+    }
+    E.peer_inbox[r] = (uint64_t*)inboxes[r] + SYNC_WORDS;
+  }
+  E.peers_open = true;
+  E.peers_direct = true;
+  return KMC_OK;
+}
+
 int kmcm_shard_sync(kmcm_ctx* c) {
   if (!c) return KMC_E_BADARG;
   CK(cudaEventRecord(E.ev_end, E.stream));
-  CK(cudaStreamSynchronize(E.stream));
+  DevCounters hc;
+  {
+    int rc = read_counters(E, &hc);              // synchronises the stream
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(E.mu);
+    E.stats.probes = hc.probes;
+    E.stats.out_of_model = hc.out_of_model;
+    E.stats.generated = hc.generated;
+    E.stats.deadlocks = hc.deadlocks;
+  }
   float total_ms = 0;
   cudaEventElapsedTime(&total_ms, E.ev_begin, E.ev_end);
   std::lock_guard<std::mutex> g(E.mu);
@@ -1946,3 +2219,193 @@ int kmcm_shard_sync(kmcm_ctx* c) {
 }
 
 }  // extern "C"
+#undef E
+
+// ----------------------------------------------------------------------------------------
+// N GPUs behind one context (kmc_create option "gpus": N): tlc2 -workers N, or any C / JNI caller.
+// The ranks are ordinary sub-contexts driven through the same kmcm_shard_* entry points the multi-process
+// driver uses; they see each other's inboxes through direct peer pointers.  Every rank thread reads the same
+// level board, so all of them take the same decisions without any host-side barrier.
+// ----------------------------------------------------------------------------------------
+static int multi_create(kmcm_ctx* c, const char* options_json, int gpus) {
+  Engine& A = c->e;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    A.last_error = "no CUDA device visible; this library has no CPU fallback";
+    return KMC_E_NO_GPU;
+  }
+  if (gpus > ndev || gpus > MAX_WORLD) {
+    A.last_error = "option gpus exceeds the visible devices";
+    return KMC_E_BADARG;
+  }
+  std::string base = options_json ? options_json : "{}";
+  size_t close = base.rfind('}');
+  if (close == std::string::npos) return KMC_E_BADARG;
+  const int dev0 = A.device;
+  for (int r = 0; r < gpus; ++r) {
+    // the sub-context's own keys go first: json_find takes the first occurrence of a key
+    std::string opt = "{\"device\": " + std::to_string(dev0 + r) + ", \"rank\": " + std::to_string(r) + ", \"world\": " +
+                      std::to_string(gpus) + ", \"gpus\": 0, " + base.substr(base.find('{') + 1);
+    kmcm_ctx* sub = nullptr;
+    int rc = kmcm_create(opt.c_str(), &sub);
+    if (sub) c->ranks.push_back(sub);
+    if (rc) {
+      A.last_error = sub ? sub->e.last_error : "cannot create a rank context";
+      return rc;
+    }
+  }
+  void* inboxes[MAX_WORLD] = {};
+  int devices[MAX_WORLD] = {};
+  for (int r = 0; r < gpus; ++r) {
+    kmcm_shard_inbox_ptr(c->ranks[r], &inboxes[r]);
+    devices[r] = dev0 + r;
+  }
+  for (int r = 0; r < gpus; ++r) {
+    int rc = kmcm_shard_open_peers_direct(c->ranks[r], inboxes, devices, (uint32_t)gpus);
+    if (rc) {
+      A.last_error = c->ranks[r]->e.last_error;
+      return rc;
+    }
+  }
+  A.world = (uint32_t)gpus;
+  return KMC_OK;
+}
+
+struct RankOutcome {
+  int rc = KMC_OK;
+  std::vector<uint64_t> levels;
+  bool stopped = false;
+  uint64_t board[MAX_WORLD * BOARD_WORDS] = {};
+};
+
+static void rank_loop(kmcm_ctx* sub, bool cont, uint64_t stop_after, RankOutcome* out) {
+  Engine& R = sub->e;
+  const uint32_t world = R.world, rank = R.rank;
+  uint64_t* board = out->board;
+  auto fail = [&](int rc) { out->rc = rc; };
+  int rc;
+  if ((rc = kmcm_shard_begin(sub))) return fail(rc);
+  if ((rc = kmcm_shard_round_p2p(sub, 0, 0, 1))) return fail(rc);
+  rc = kmcm_shard_level_sync(sub, board);
+  uint64_t first = 0;
+  for (;;) {
+    // a failure flag of ANY rank ends the run on every rank (they all read the same board)
+    int err = rc;
+    uint64_t total = 0, viol = 0, max_new = 0, distinct = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+      const uint64_t* b = board + r * BOARD_WORDS;
+      total += b[1];
+      viol += b[2];
+      distinct += b[3];
+      max_new = std::max(max_new, b[1]);
+      if (!err && b[5]) err = fail_to_error(b[5]);
+    }
+    if (err) return fail(err);
+    if (viol && !cont) { out->stopped = true; break; }
+    if (total == 0) break;
+    out->levels.push_back(total);
+    if (stop_after && distinct >= stop_after) { out->stopped = true; break; }
+    const uint64_t count = board[rank * BOARD_WORDS + 1];
+    const uint64_t n_chunks = (max_new + R.chunk_states - 1) / R.chunk_states;
+    for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+      const uint64_t off = ci * R.chunk_states;
+      const uint64_t n = off < count ? std::min<uint64_t>(R.chunk_states, count - off) : 0;
+      if ((rc = kmcm_shard_round_p2p(sub, first + off, n, 0))) return fail(rc);
+    }
+    first += count;
+    rc = kmcm_shard_level_sync(sub, board);
+  }
+  if ((rc = kmcm_shard_sync(sub))) return fail(rc);
+}
+
+static int multi_run(kmcm_ctx* c) {
+  Engine& A = c->e;
+  const size_t n = c->ranks.size();
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<RankOutcome> out(n);
+  std::vector<std::thread> th;
+  for (size_t r = 0; r < n; ++r) th.emplace_back(rank_loop, c->ranks[r], A.cont, A.stop_after_states, &out[r]);
+  for (auto& t : th) t.join();
+  auto t1 = std::chrono::steady_clock::now();
+  int rc = KMC_OK;
+  for (size_t r = 0; r < n; ++r)
+    if (out[r].rc && !rc) {
+      rc = out[r].rc;
+      A.last_error = c->ranks[r]->e.last_error;
+    }
+  std::lock_guard<std::mutex> g(A.mu);
+  kmc_stats_t& st = A.stats;
+  memset(&st, 0, sizeof(st));
+  A.widths = out[0].levels;
+  for (size_t r = 0; r < n; ++r) {
+    const kmc_stats_t& s = c->ranks[r]->e.stats;
+    st.distinct += s.distinct;
+    st.generated += s.generated;
+    st.deadlocks += s.deadlocks;
+    st.out_of_model += s.out_of_model;
+    st.probes += s.probes;
+    st.table_slots += s.table_slots;
+    st.max_states += s.max_states;
+    st.launches_expand += s.launches_expand;
+    st.launches_insert += s.launches_insert;
+    st.launches_other += s.launches_other;
+    st.gpu_ms_total = std::max(st.gpu_ms_total, s.gpu_ms_total);
+    st.gpu_ms_expand = std::max(st.gpu_ms_expand, s.gpu_ms_expand);
+    st.gpu_ms_insert = std::max(st.gpu_ms_insert, s.gpu_ms_insert);
+    st.gpu_ms_invariant = std::max(st.gpu_ms_invariant, s.gpu_ms_invariant);
+    st.slot_bytes = s.slot_bytes;
+  }
+  st.depth = st.levels = A.widths.size();
+  st.complete = (!rc && !out[0].stopped) ? 1 : 0;
+  if (out[0].stopped && !rc) {
+    // the states of the last level were inserted but not expanded: they are the queue
+    for (size_t r = 0; r < n; ++r) st.queue += out[0].board[r * BOARD_WORDS + 1];
+  }
+  st.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  // violation: deadlocks (they belong to the level being expanded) before invariant violations, then the smallest
+  // fingerprint, then the rank -- the single-GPU rule -- and the parent links are followed from store to store
+  memset(&A.viol, 0, sizeof(A.viol));
+  A.viol.invariant = -1;
+  A.trace.clear();
+  A.trace_actions.clear();
+  const Engine* best = nullptr;
+  for (size_t r = 0; r < n; ++r) {
+    const Engine& R = c->ranks[r]->e;
+    if (R.viol.kind == KMC_RESULT_OK) continue;
+    if (!best) { best = &R; continue; }
+    const bool rd = R.viol.kind == KMC_RESULT_DEADLOCK, bd = best->viol.kind == KMC_RESULT_DEADLOCK;
+    if (rd != bd) { if (rd) best = &R; continue; }
+    if (R.viol.fingerprint < best->viol.fingerprint) best = &R;
+  }
+  if (best && !rc) {
+    std::vector<std::vector<uint64_t>> rev;
+    std::vector<uint32_t> rev_act;
+    uint64_t meta = best->viol_meta;
+    rev.push_back(best->viol_words);
+    rev_act.push_back((uint32_t)(meta >> 56));
+    uint64_t guard = 0;
+    while ((meta & 0x0000FFFFFFFFFFFFull) != NO_PARENT && guard++ < 100000) {
+      const uint64_t idx = meta & IDX_MASK;
+      const uint32_t prank = (uint32_t)((meta >> 40) & 0xFF);
+      if (prank >= n) break;
+      const Engine& P = c->ranks[prank]->e;
+      if (idx >= P.max_states) break;
+      std::vector<uint64_t> sw(W);
+      if (cudaSetDevice(P.device) != cudaSuccess ||
+          cudaMemcpy(sw.data(), P.store + idx * W, W * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(&meta, P.parent + idx, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+        break;
+      rev.push_back(sw);
+      rev_act.push_back((uint32_t)(meta >> 56));
+    }
+    A.trace.assign(rev.rbegin(), rev.rend());
+    A.trace_actions.assign(rev_act.rbegin(), rev_act.rend());
+    A.viol = best->viol;
+    A.viol.trace_len = A.trace.size();
+    A.viol_words = best->viol_words;
+    A.viol_meta = best->viol_meta;
+  }
+  A.ran = true;
+  return rc;
+}
+

@@ -50,6 +50,10 @@ struct kmc_ctx {
   int (*shard_seed_p2p)(kmcm_ctx*) = nullptr;
   int (*shard_expand_p2p)(kmcm_ctx*, uint64_t, uint64_t) = nullptr;
   int (*shard_insert_p2p)(kmcm_ctx*) = nullptr;
+  int (*shard_round_p2p)(kmcm_ctx*, uint64_t, uint64_t, int) = nullptr;
+  int (*shard_level_sync)(kmcm_ctx*, uint64_t*) = nullptr;
+  int (*shard_inbox_ptr)(kmcm_ctx*, void**) = nullptr;
+  int (*shard_open_peers_direct)(kmcm_ctx*, void* const*, const int*, uint32_t) = nullptr;
 };
 
 template <class F>
@@ -88,7 +92,9 @@ int kmc_create(const char* model_lib, const char* options_json, kmc_ctx** out) {
             bind(c, c->shard_insert, "kmcm_shard_insert") && bind(c, c->shard_level_done, "kmcm_shard_level_done") &&
             bind(c, c->shard_sync, "kmcm_shard_sync") && bind(c, c->shard_ipc_handle, "kmcm_shard_ipc_handle") &&
             bind(c, c->shard_open_peers, "kmcm_shard_open_peers") && bind(c, c->shard_seed_p2p, "kmcm_shard_seed_p2p") &&
-            bind(c, c->shard_expand_p2p, "kmcm_shard_expand_p2p") && bind(c, c->shard_insert_p2p, "kmcm_shard_insert_p2p");
+            bind(c, c->shard_expand_p2p, "kmcm_shard_expand_p2p") && bind(c, c->shard_insert_p2p, "kmcm_shard_insert_p2p") &&
+            bind(c, c->shard_round_p2p, "kmcm_shard_round_p2p") && bind(c, c->shard_level_sync, "kmcm_shard_level_sync") &&
+            bind(c, c->shard_inbox_ptr, "kmcm_shard_inbox_ptr") && bind(c, c->shard_open_peers_direct, "kmcm_shard_open_peers_direct");
   if (!ok) return KMC_E_MODEL;
   return c->create(options_json, &c->inner);
 }
@@ -138,5 +144,11 @@ int kmc_shard_open_peers(kmc_ctx* c, const void* h, uint32_t world) { FWD(shard_
 int kmc_shard_seed_p2p(kmc_ctx* c) { FWD(shard_seed_p2p); }
 int kmc_shard_expand_p2p(kmc_ctx* c, uint64_t first, uint64_t count) { FWD(shard_expand_p2p, first, count); }
 int kmc_shard_insert_p2p(kmc_ctx* c) { FWD(shard_insert_p2p); }
+int kmc_shard_round_p2p(kmc_ctx* c, uint64_t first, uint64_t count, int seed) { FWD(shard_round_p2p, first, count, seed); }
+int kmc_shard_level_sync(kmc_ctx* c, uint64_t* board) { FWD(shard_level_sync, board); }
+int kmc_shard_inbox_ptr(kmc_ctx* c, void** out) { FWD(shard_inbox_ptr, out); }
+int kmc_shard_open_peers_direct(kmc_ctx* c, void* const* inboxes, const int* devices, uint32_t world) {
+  FWD(shard_open_peers_direct, inboxes, devices, world);
+}
 
 }  // extern "C"

@@ -502,7 +502,7 @@ struct State {{ uint64_t w[W]; }};
 
 
 def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | None = None,
-                group_lines: int = 160, max_group_sites: int = 64, guard_lines: int = 400) -> LoweredModel:
+                group_lines: int = 160, max_group_sites: int = 64, guard_lines: int = 3000) -> LoweredModel:
     cfg = parse_cfg(cfg_text)
     root = load_root(module, search_dirs)
     lw = Lowerer(root, cfg)

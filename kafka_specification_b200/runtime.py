@@ -110,12 +110,17 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.kmc_shard_seed_p2p.argtypes = [vp]
     lib.kmc_shard_expand_p2p.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64]
     lib.kmc_shard_insert_p2p.argtypes = [vp]
+    lib.kmc_shard_round_p2p.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]
+    lib.kmc_shard_level_sync.argtypes = [vp, u64p]
+    lib.kmc_shard_inbox_ptr.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.kmc_shard_open_peers_direct.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_uint32]
     for fn in ("kmc_create", "kmc_model_info", "kmc_run", "kmc_stats", "kmc_level_widths", "kmc_action_counts",
                "kmc_violation", "kmc_trace_state", "kmc_copy_states", "kmc_copy_parents", "kmc_violation_record", "kmc_fpset_put", "kmc_fpset_contains",
                "kmc_fpset_size", "kmc_shard_begin", "kmc_shard_buffers", "kmc_shard_seed_init", "kmc_shard_expand",
                "kmc_shard_counts", "kmc_shard_reset_cand", "kmc_shard_insert", "kmc_shard_level_done", "kmc_shard_sync",
                "kmc_shard_ipc_handle", "kmc_shard_open_peers", "kmc_shard_seed_p2p", "kmc_shard_expand_p2p",
-               "kmc_shard_insert_p2p"):
+               "kmc_shard_insert_p2p", "kmc_shard_round_p2p", "kmc_shard_level_sync", "kmc_shard_inbox_ptr",
+               "kmc_shard_open_peers_direct"):
         getattr(lib, fn).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -306,7 +311,7 @@ class Checker:
             self.meta = json.load(f)
         self.decoder = StateDecoder(self.meta)
         self.ctx = ctypes.c_void_p()
-        opts = {("continue" if k == "cont" else k): v for k, v in options.items() if k != "p2p"}
+        opts = {("continue" if k == "cont" else k): v for k, v in options.items() if k not in ("p2p", "device_sync")}
         rc = self.lib.kmc_create(self.model_lib.encode(), json.dumps(opts).encode(), ctypes.byref(self.ctx))
         if rc != 0:
             msg = self.lib.kmc_strerror(self.ctx, rc).decode() if self.ctx else "kmc_create failed"

@@ -90,6 +90,7 @@ class CudaShardEngine(ShardEngine):
         self.counts_dev = torch.as_tensor(_DevArray(b.cand_counts, 8), device=self.device)[:world]
         self._matrix = torch.empty(world * world, dtype=torch.int64, device=self.device)
         self.p2p = False
+        self.device_sync = bool(options.get("device_sync", True))
         if world > 1 and options.get("p2p", True) and dist.is_initialized():
             self._open_peers()
 
@@ -117,6 +118,16 @@ class CudaShardEngine(ShardEngine):
 
     def insert_p2p(self):
         self.ck._check(self.lib.kmc_shard_insert_p2p(self.ck.ctx))
+
+    def round_p2p(self, first, count, seed=False):
+        self.ck._check(self.lib.kmc_shard_round_p2p(self.ck.ctx, first, count, 1 if seed else 0))
+
+    def level_sync(self):
+        """Level end with device-side synchronisation: returns the board, one row per rank:
+        [level id, new states, violations, store tail, generated, fail, deadlocks, -]."""
+        buf = (ctypes.c_uint64 * (8 * self.world))()
+        self.ck._check(self.lib.kmc_shard_level_sync(self.ck.ctx, buf))
+        return [[int(buf[r * 8 + k]) for k in range(8)] for r in range(self.world)]
 
     def barrier_on_stream(self, group=None):
         """Cross-rank barrier ordered on the engine's stream; the host does not wait."""
@@ -312,8 +323,47 @@ class ShardedChecker:
                 return self._run()
         return self._run()
 
+    def _run_device_sync(self) -> ShardedResult:
+        """The fused path with device-side synchronisation: per level one host synchronisation (the level board)
+        and no collective; per round no host wait at all (kmc_shard_round_p2p)."""
+        e = self.e
+        self.exchanged = 0
+        dist.barrier(group=self.group)
+        t0 = time.perf_counter()
+        e.begin()
+        e.round_p2p(0, 0, seed=True)
+        board = e.level_sync()
+        first, levels, stopped = 0, [], False
+        while True:
+            count = board[self.rank][1]
+            total = sum(b[1] for b in board)
+            if any(b[2] for b in board) and not self.cont:
+                stopped = True
+                break
+            if total == 0:
+                break
+            levels.append(total)
+            n_chunks = max((b[1] + e.chunk_states - 1) // e.chunk_states for b in board)
+            for c in range(n_chunks):
+                off = c * e.chunk_states
+                e.round_p2p(first + off, max(0, min(e.chunk_states, count - off)))
+            first += count
+            board = e.level_sync()
+        e.finish()
+        st = e.stats()
+        rows = [[b[3], b[4], b[6]] for b in board]
+        seconds = self._all_reduce_max_float(time.perf_counter() - t0)
+        any_viol = any(b[2] for b in board)
+        viol, trace = (self._global_violation() if any_viol else (None, []))
+        return ShardedResult(distinct=sum(r[0] for r in rows), generated=sum(r[1] for r in rows), depth=len(levels),
+                             deadlocks=sum(r[2] for r in rows), levels=levels, complete=not stopped,
+                             violation=viol, per_rank_distinct=[r[0] for r in rows], seconds=seconds,
+                             exchanged_rows=sum(r[1] for r in rows), stats=st, trace=trace)
+
     def _run(self) -> ShardedResult:
         e = self.e
+        if getattr(e, "p2p", False) and getattr(e, "device_sync", True) and hasattr(e, "round_p2p"):
+            return self._run_device_sync()
         self.exchanged = 0
         if self.world > 1:
             dist.barrier(group=self.group)

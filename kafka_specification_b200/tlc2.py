@@ -7,7 +7,9 @@
 from the same directory (and ``-I`` directories), like TLC does.  The spec and its ``.cfg`` are
 lowered ahead of time into a CUDA switch table (cached under ``build/models/``), the BFS runs on
 the GPU through ``libkspecmc.so``, and the summary / error trace are printed in TLC's format.
-``-workers`` is accepted for compatibility (the GPU grid replaces TLC's worker threads).
+``-workers N`` selects N GPUs of this machine (fingerprint-sharded inside the library, option ``"gpus": N`` of
+kmc_create); ``-workers auto`` = one GPU (the GPU grid replaces TLC's worker threads).  ``-tool`` wraps the
+messages in TLC's tool-mode markers (``@!@!@STARTMSG code:class @!@!@`` ... ``@!@!@ENDMSG code @!@!@``).
 
 Exit status follows TLC: 0 no error, 12 safety (invariant) violation, 11 deadlock,
 10 assumption failure, 150 spec/config error, 1 runtime failure (no GPU, table full, ...).
@@ -54,6 +56,24 @@ def parse_args(argv):
     return ap.parse_args(argv)
 
 
+# TLC's -tool mode wraps every message as  @!@!@STARTMSG <code>:<class> @!@!@ / text / @!@!@ENDMSG <code> @!@!@
+# (class 0 = info, 1 = error, 4 = a state of an error trace).  The codes are those of TLC's tlc2.output.EC as
+# published (TLC is not in the reference tree and cannot run here, so they are reproduced, not verified).
+EC = {"version": 2262, "mode": 2187, "sany_start": 2220, "sany_end": 2219, "starting": 2185, "init": 2189,
+      "init_done": 2190, "inv_initial": 2107, "inv_behavior": 2110, "deadlock": 2114, "behavior": 2121,
+      "state": 2217, "success": 2193, "collision": 2201, "stats": 2199, "depth": 2194, "finished": 2186,
+      "general": 1000}
+_TOOL = False
+
+
+def msg(kind: str, text: str, cls: int = 0):
+    if _TOOL:
+        code = EC[kind]
+        print(f"@!@!@STARTMSG {code}:{cls} @!@!@\n{text}\n@!@!@ENDMSG {code} @!@!@")
+    else:
+        print(text)
+
+
 def collision_probability(distinct: int, generated: int) -> float:
     """TLC's 'calculated (optimistic)' estimate: n * (g - n) / 2^64."""
     return distinct * max(generated - distinct, 1) / 2.0 ** 64
@@ -77,8 +97,16 @@ def main(argv=None) -> int:
     if not cfg_path.endswith(".cfg"):
         cfg_path += ".cfg"
     t0 = time.time()
-    print("TLC2-compatible front end of kspec-mc (B200-native explicit-state model checker)")
-    print(f"Running breadth-first search Model-Checking on the GPU (-workers {a.workers} accepted, unused).")
+    global _TOOL
+    _TOOL = bool(a.tool)
+    msg("version", "TLC2-compatible front end of kspec-mc (B200-native explicit-state model checker)")
+    try:
+        n_gpus = 1 if a.workers == "auto" else max(1, int(a.workers))
+    except ValueError:
+        print(f"Error: -workers takes a number or auto, not {a.workers!r}")
+        return EXIT_ERROR_SPEC
+    msg("mode", f"Running breadth-first search Model-Checking on {n_gpus} GPU{'s' if n_gpus > 1 else ''} "
+                f"(-workers {a.workers}).")
     try:
         cfg_text = open(cfg_path).read()
     except OSError as e:
@@ -87,23 +115,25 @@ def main(argv=None) -> int:
     os.environ["KSPEC_TLA_PATH"] = os.pathsep.join([spec_dir] + a.I + [os.environ.get("KSPEC_TLA_PATH", "")]).strip(os.pathsep)
     name = re.sub(r"[^A-Za-z0-9_]", "_", module).lower() + "_" + hashlib.sha256(cfg_text.encode()).hexdigest()[:10]
     try:
-        print(f"Parsing file {os.path.join(spec_dir, module + '.tla')}")
+        msg("sany_start", f"Parsing file {os.path.join(spec_dir, module + '.tla')}")
         model = B.lower_to_dir(module, cfg_path, name)
         for w in model.warnings:
             if not a.nowarning:
                 print(f"Warning: {w}")
-        print(f"Semantic processing of module {module}")
+        msg("sany_end", f"Semantic processing of module {module}")
         B.build_dispatcher()
         B.compile_model(name)
     except (TlaSyntaxError, ModuleError, CfgError) as e:
-        print(f"Error: {e}")
+        msg("general", f"Error: {e}", 1)
         return EXIT_ERROR_SPEC
     except LowerError as e:
         msg = str(e)
-        print(f"Error: {msg}")
+        msg("general", f"Error: {msg}", 1)
         return EXIT_VIOLATION_ASSUMPTION if "ASSUME" in msg else EXIT_ERROR_SPEC
-    print(f"Starting... ({time.strftime('%Y-%m-%d %H:%M:%S')})")
+    msg("starting", f"Starting... ({time.strftime('%Y-%m-%d %H:%M:%S')})")
     opts = {"device": a.device}
+    if n_gpus > 1:
+        opts["gpus"] = n_gpus
     if a.fpbits:
         opts["table_log2"] = a.fpbits
     if a.maxstates:
@@ -115,9 +145,9 @@ def main(argv=None) -> int:
     try:
         ck = Checker(name, **opts)
     except KmcError as e:
-        print(f"Error: {e}")
+        msg("general", f"Error: {e}", 1)
         return 1
-    print("Computing initial states...")
+    msg("init", "Computing initial states...")
     try:
         r = ck.run(raise_on_error=False)
         st = r.stats
@@ -125,43 +155,42 @@ def main(argv=None) -> int:
             print(f"Error: {ck.error_text(ck.last_rc)}")
             return 1
     except KmcError as e:
-        print(f"Error: {e}")
+        msg("general", f"Error: {e}", 1)
         return 1
     n_init = len(model.init_states)
-    print(f"Finished computing initial states: {n_init} distinct state{'s' if n_init != 1 else ''} generated.")
+    msg("init_done", f"Finished computing initial states: {n_init} distinct state{'s' if n_init != 1 else ''} generated.")
     exit_code = EXIT_OK
     if r.violation:
         v = r.violation
         if v["kind"] == "deadlock":
-            print("Error: Deadlock reached.")
+            msg("deadlock", "Error: Deadlock reached.", 1)
             exit_code = EXIT_VIOLATION_DEADLOCK
         elif v["level"] == 1:
-            print(f"Error: Invariant {v['invariant']} is violated by the initial state:")
+            msg("inv_initial", f"Error: Invariant {v['invariant']} is violated by the initial state:", 1)
             exit_code = EXIT_VIOLATION_SAFETY
         else:
-            print(f"Error: Invariant {v['invariant']} is violated.")
+            msg("inv_behavior", f"Error: Invariant {v['invariant']} is violated.", 1)
             exit_code = EXIT_VIOLATION_SAFETY
         if v["level"] != 1 or v["kind"] == "deadlock":
-            print("Error: The behavior up to this point is:")
+            msg("behavior", "Error: The behavior up to this point is:", 1)
         for i, t in enumerate(r.trace):
-            print(f"State {i + 1}: {action_location(t['action'])}")
-            print(t["text"])
-            print()
+            msg("state", f"State {i + 1}: {action_location(t['action'])}\n{t['text']}\n", 4)
     else:
-        print("Model checking completed. No error has been found.")
-        print("  Estimates of the probability that TLC did not check all reachable states")
-        print("  because two distinct states had the same fingerprint:")
+        msg("success", "Model checking completed. No error has been found.\n"
+                       "  Estimates of the probability that TLC did not check all reachable states\n"
+                       "  because two distinct states had the same fingerprint:")
         if ck.info.exact:
-            print("  calculated (optimistic):  val = 0 (states fit 63 bits: the fingerprint is a bijection)")
+            msg("collision", "  calculated (optimistic):  val = 0 (the set key is a bijection of the packed state: exact)")
         else:
-            print(f"  calculated (optimistic):  val = {collision_probability(r.distinct, r.generated):.1E}")
-    print(f"{r.generated} states generated, {r.distinct} distinct states found, {r.queue} states left on queue.")
+            p128 = collision_probability(r.distinct, r.generated) / 2.0 ** 65
+            msg("collision", f"  calculated (optimistic):  val = {p128:.1E} (128-bit fingerprints)")
+    msg("stats", f"{r.generated} states generated, {r.distinct} distinct states found, {r.queue} states left on queue.")
     if r.complete:
-        print(f"The depth of the complete state graph search is {r.depth}.")
+        msg("depth", f"The depth of the complete state graph search is {r.depth}.")
     dt = time.time() - t0
-    print(f"Finished in {int(dt // 60):02d}min {int(dt % 60):02d}s at ({time.strftime('%Y-%m-%d %H:%M:%S')}); "
-          f"GPU search time {st['gpu_ms_total']:.1f} ms "
-          f"({r.distinct / max(st['gpu_ms_total'], 1e-6) * 1000:.3g} distinct states/s)")
+    msg("finished", f"Finished in {int(dt // 60):02d}min {int(dt % 60):02d}s at ({time.strftime('%Y-%m-%d %H:%M:%S')}); "
+                    f"GPU search time {st['gpu_ms_total']:.1f} ms "
+                    f"({r.distinct / max(st['gpu_ms_total'], 1e-6) * 1000:.3g} distinct states/s)")
     ck.close()
     return exit_code
 

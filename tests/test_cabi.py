@@ -99,3 +99,31 @@ def test_product_never_imports_the_oracle():
                 if "oracle" not in low:
                     continue
                 assert not re.search(r"\b(import|from|include|cdll|dlopen|subprocess|open)\b", low), (f, line.strip())
+
+
+@pytest.mark.gpu
+def test_two_gpus_behind_kmc_create_and_kmc_run_only(goldens):
+    """One kmc_ctx drives several GPUs (option "gpus"): no torch, no NCCL, no second process -- host threads inside
+    the library, peers mapped with cudaDeviceEnablePeerAccess, device-side round/level synchronisation."""
+    import ctypes
+    import json
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libkspecmc.so"))
+    ndev = ctypes.c_int(0)
+    cudart = ctypes.CDLL("libcudart.so")
+    cudart.cudaGetDeviceCount(ctypes.byref(ndev))
+    if ndev.value < 2:
+        pytest.skip("needs 2 GPUs")
+    from kafka_specification_b200.runtime import Checker
+    g = goldens["kip320_small"]
+    with Checker("kip320_small", gpus=2, table_log2=22, cont=True) as ck:
+        r = ck.run()
+    assert r.complete and r.violation is None
+    assert (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
+        g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+    # a violating model: same verdict, level and a complete trace across the two stores
+    g = goldens["trunchw_small"]
+    first = min(l for l in g["first_violation_level"].values() if l)
+    with Checker("trunchw_small", gpus=2, table_log2=22) as ck:
+        r = ck.run()
+    assert not r.complete and r.violation["kind"] == "invariant" and r.violation["level"] == first
+    assert len(r.trace) == first and r.trace[0]["action"] is None

@@ -71,3 +71,30 @@ def test_cli_end_to_end_on_gpu(tmp_path):
     assert rc == 11 and "Error: Deadlock reached." in out and "State 4: <Next" in out
     rc, out = run_cli("-deadlock", str(dl))
     assert rc == 0 and "4 distinct states found" in out
+
+
+@pytest.mark.gpu
+def test_cli_tool_mode_wraps_messages_in_tlc_markers(tmp_path):
+    """-tool: every message carries TLC's @!@!@STARTMSG code:class / @!@!@ENDMSG code markers; trace states are class 4."""
+    dl = tmp_path / "Stop.tla"
+    dl.write_text("---- MODULE Stop ----\nEXTENDS Integers\nVARIABLE x\nInit == x = 0\nNext == x < 3 /\\ x' = x + 1\n"
+                  "TypeOk == x \\in 0 .. 3\n====\n")
+    (tmp_path / "Stop.cfg").write_text("INIT Init\nNEXT Next\nINVARIANT TypeOk\n")
+    rc, out = run_cli("-tool", str(dl))
+    assert rc == 11
+    assert "@!@!@STARTMSG 2114:1 @!@!@\nError: Deadlock reached.\n@!@!@ENDMSG 2114 @!@!@" in out
+    assert out.count("@!@!@STARTMSG 2217:4 @!@!@") == 4 and "@!@!@STARTMSG 2199:0 @!@!@" in out
+    assert out.count("@!@!@STARTMSG") == out.count("@!@!@ENDMSG")
+
+
+@pytest.mark.gpu
+def test_cli_workers_n_runs_on_n_gpus(tmp_path):
+    """-workers 2: the library shards the search over two GPUs of this process (kmc_create option gpus)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rc, out = run_cli("-workers", "2", "-config", os.path.join(SPECS, "MiniLock.cfg"), "-deadlock", os.path.join(SPECS, "MiniLock"))
+    assert rc == 0, out
+    assert "on 2 GPUs" in out
+    assert "169 states generated, 76 distinct states found, 0 states left on queue." in out
+    assert "The depth of the complete state graph search is 14." in out
