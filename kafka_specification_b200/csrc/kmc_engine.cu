@@ -183,7 +183,9 @@ struct Params {
   uint64_t bucket_mask;     // #buckets - 1
   uint64_t* store;
   uint64_t* parent;
-  uint64_t max_states;
+  uint64_t max_states;      // capacity of the device-resident store (a ring when spilling)
+  uint64_t store_mask;      // spill: max_states - 1 (power of two), device slot = global index & mask; else ~0
+  uint64_t store_base;      // spill: global index of the oldest state still on the device (older ones are on the host)
   uint64_t* cand;
   uint64_t region_rows;
   DevCounters* ctr;
@@ -382,11 +384,11 @@ __device__ __forceinline__ void insert_row(const Params& p, const State& s, uint
     base = __shfl_sync(0xffffffffu, base, leader);
     if (is_new) {
       uint64_t idx = base + __popc(mask & ((1u << lane) - 1));
-      if (idx < p.max_states) {
-        uint64_t* dst = p.store + idx * W;
+      if (idx - p.store_base < p.max_states) {
+        uint64_t* dst = p.store + (idx & p.store_mask) * W;
 #pragma unroll
         for (int k = 0; k < W; ++k) dst[k] = s.w[k];
-        p.parent[idx] = meta;
+        p.parent[idx & p.store_mask] = meta;
       } else {
         failed = KMC_FAIL_STORE_FULL;
       }
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_CTAS_PER_SM) k_expand(Par
     if (threadIdx.x < 3 * MAX_GROUP_SITES) sts32(c.cnt + threadIdx.x * 4, 0u);      // cnt[2][64] and cur[64]
     {
       // frontier tile -> shared memory, coalesced (128-bit loads when the rows are 16-byte aligned)
-      const uint64_t* src = p.store + (first + tile_base) * W;
+      const uint64_t* src = p.store + ((first + tile_base) & p.store_mask) * W;      // (a chunk never crosses the ring's wrap)
       const unsigned nwords = c.nvalid * W;
       if (((W & 1) == 0)) {
         const ulonglong2* src2 = reinterpret_cast<const ulonglong2*>(src);
@@ -815,8 +817,9 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, EXPAND_CTAS_PER_SM) k_expand(Par
           ++dead;
           if (p.check_deadlock) {
             State s;
-            load_state(s, p.store + (first + tile_base + slot) * W);
-            record_violation(p, s, p.parent[first + tile_base + slot], fingerprint(s), ~0ull);
+            const uint64_t gi = (first + tile_base + slot) & p.store_mask;
+            load_state(s, p.store + gi * W);
+            record_violation(p, s, p.parent[gi], fingerprint(s), ~0ull);
           }
         }
       }
@@ -856,7 +859,7 @@ struct GroupRunner {
         uint64_t i = tile_base + (uint64_t)j * EXPAND_BLOCK + threadIdx.x;
         if (i < count) {
           State s;
-          load_state(s, p.store + (first + i) * W);
+          load_state(s, p.store + ((first + i) & p.store_mask) * W);
           CandSink sink{(first + i) | ((uint64_t)p.rank << 40), wbuf, wcnt, p.count_actions ? p.ctr->action_counts : nullptr, 0, 0,
                         p.world == 1 ? p.cand : nullptr, &p.ctr->cand_count[p.cand_slot], p.region_rows};
           M::expand_group(M::GroupTag<G>{}, s, sink);
@@ -902,8 +905,8 @@ __global__ void __launch_bounds__(EXPAND_BLOCK, 1) k_expand1(Params p, uint64_t 
         ++dead;
         if (p.check_deadlock) {
           State s;
-          load_state(s, p.store + (first + i) * W);
-          record_violation(p, s, p.parent[first + i], fingerprint(s), ~0ull);
+          load_state(s, p.store + ((first + i) & p.store_mask) * W);
+          record_violation(p, s, p.parent[(first + i) & p.store_mask], fingerprint(s), ~0ull);
         }
       }
     }
@@ -1096,16 +1099,30 @@ __global__ void __launch_bounds__(256) k_insert_inbox(Params p) {
 // has work (inside k_insert only the ~1/3 of lanes holding a new state would be active).
 __global__ void __launch_bounds__(256) k_invariants(Params p, uint64_t first, const unsigned long long* end_ptr) {
   uint64_t end = (uint64_t)*end_ptr;
-  if (end > p.max_states) end = p.max_states;
+  if (end - p.store_base > p.max_states) end = p.store_base + p.max_states;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
     State s;
-    const uint64_t* src = p.store + i * W;
+    const uint64_t* src = p.store + (i & p.store_mask) * W;
 #pragma unroll
     for (int k = 0; k < W; ++k) s.w[k] = __ldcs(src + k);
     int inv = M::first_violated_invariant(s);
-    if (inv >= 0) record_violation(p, s, p.parent[i], fingerprint(s), (uint64_t)inv);
+    if (inv >= 0) record_violation(p, s, p.parent[i & p.store_mask], fingerprint(s), (uint64_t)inv);
   }
+}
+
+// -recover: the set is not part of a checkpoint; it is rebuilt from the stored states (one insert each)
+__global__ void __launch_bounds__(256) k_rebuild(Params p, const uint64_t* states, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  int failed = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    State s;
+#pragma unroll
+    for (int k = 0; k < W; ++k) s.w[k] = states[i * W + k];
+    unsigned probes = 0;
+    if (set_insert(p.table, p.bucket_mask, state_ident(s), probes) < 0) failed = KMC_FAIL_TABLE_FULL;
+  }
+  if (failed) atomicCAS(&p.ctr->fail, 0ull, (unsigned long long)failed);
 }
 
 // The set alone (FPSet.put / contains): the caller's 64-bit fingerprints are the identities; with 16-byte
@@ -1151,6 +1168,14 @@ struct Engine {
   uint64_t stop_after_states = 0;   // bounded run: stop at the first level end with >= this many states
   int l2_fetch = 0;                 // cudaLimitMaxL2FetchGranularity hint (32/64/128), 0 = leave the default
   uint32_t fanout_bound = 0;        // successors per state assumed when sizing a frontier chunk (0: min(MAX_FANOUT, 32))
+  // spill / checkpoint (single rank): the device store is a ring over the live window [store_base, tail); the
+  // levels below the one being expanded move to host memory (TLC's DiskStateQueue / trace file on disk)
+  bool spill = false;
+  uint64_t store_base = 0;
+  std::vector<uint64_t> host_store, host_parent;
+  std::string checkpoint_dir, recover_dir;
+  double checkpoint_minutes = 0;    // 0: a checkpoint after every level (when checkpoint_dir is set)
+  std::chrono::steady_clock::time_point last_checkpoint;
   bool overlap = false;             // single rank: K2 of chunk i runs on a second stream while K1 expands chunk i+1
                                     // (K1 is issue-bound, K2 waits on random DRAM sectors: they use different units)
   cudaStream_t stream2 = nullptr;
@@ -1211,6 +1236,8 @@ struct Engine {
     p.store = store;
     p.parent = parent;
     p.max_states = max_states;
+    p.store_mask = spill ? max_states - 1 : ~0ull;
+    p.store_base = store_base;
     p.cand = cand;
     p.region_rows = region_rows;
     p.ctr = ctr;
@@ -1266,6 +1293,14 @@ static bool json_num(const char* js, const char* key, double* out) {
   double d = strtod(v, &end);
   if (end == v) return false;
   *out = d;
+  return true;
+}
+static bool json_str(const char* js, const char* key, std::string* out) {
+  const char* v;
+  if (!json_find(js, key, &v) || *v != '"') return false;
+  const char* e = strchr(v + 1, '"');
+  if (!e) return false;
+  out->assign(v + 1, e);
   return true;
 }
 static bool json_bool(const char* js, const char* key, bool* out) {
@@ -1348,11 +1383,21 @@ static int engine_alloc(Engine& E) {
     while (lg < 34 && (1ull << lg) < (uint64_t)(2.5 * (double)E.max_states)) ++lg;
     E.table_log2 = lg;
   }
+  if (E.spill && E.max_states) {
+    uint64_t p2 = 1;
+    while (p2 * 2 <= E.max_states) p2 *= 2;
+    E.max_states = p2;                                  // the spilling store is a power-of-two ring
+  }
   E.table_slots = 1ull << E.table_log2;
   if (E.max_states == 0) {
     const uint64_t table_bytes = E.table_slots * SLOT_BYTES;
     const uint64_t room = budget > table_bytes ? (budget - table_bytes) / per_state : 0;
     E.max_states = std::max<uint64_t>(1024, std::min<uint64_t>(E.table_slots / 2, room));
+    if (E.spill) {
+      uint64_t p2 = 1;
+      while (p2 * 2 <= E.max_states) p2 *= 2;
+      E.max_states = p2;
+    }
   }
   uint64_t rows_total = E.cand_bytes / (ROW * 8);
   if (E.world > 1) E.overlap = false;                    // (the fused exchange double-buffers on its own)
@@ -1420,6 +1465,9 @@ static int engine_reset(Engine& E) {
   E.viol.invariant = -1;
   E.level_first = E.level_count = 0;
   E.shard_levels = 0;
+  E.store_base = 0;
+  E.host_store.clear();
+  E.host_parent.clear();
   return KMC_OK;
 }
 
@@ -1522,6 +1570,174 @@ static int reset_cand(Engine& E) {
   return KMC_OK;
 }
 
+// State / parent word by GLOBAL index: from the host spill below store_base, else from the device ring.
+static int fetch_state(Engine& E, uint64_t idx, uint64_t* words, uint64_t* meta) {
+  if (idx < E.store_base) {
+    memcpy(words, E.host_store.data() + idx * W, W * 8);
+    *meta = E.host_parent[idx];
+    return KMC_OK;
+  }
+  const uint64_t slot = E.spill ? (idx & (E.max_states - 1)) : idx;
+  CK(cudaMemcpy(words, E.store + slot * W, W * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(meta, E.parent + slot, 8, cudaMemcpyDeviceToHost));
+  return KMC_OK;
+}
+
+// device ring range [first, first + count) (global indices, all on the device) -> host buffers
+static int copy_ring_range(Engine& E, uint64_t first, uint64_t count, uint64_t* states, uint64_t* parents) {
+  uint64_t done = 0;
+  while (done < count) {
+    const uint64_t g = first + done;
+    const uint64_t slot = E.spill ? (g & (E.max_states - 1)) : g;
+    const uint64_t n = E.spill ? std::min<uint64_t>(count - done, E.max_states - slot) : count - done;
+    if (states) CK(cudaMemcpy(states + done * W, E.store + slot * W, n * W * 8, cudaMemcpyDeviceToHost));
+    if (parents) CK(cudaMemcpy(parents + done, E.parent + slot, n * 8, cudaMemcpyDeviceToHost));
+    done += n;
+  }
+  return KMC_OK;
+}
+
+// Spill: everything below the level that is expanded next moves to host memory and its ring slots become free.
+static int spill_below(Engine& E, uint64_t level_first) {
+  if (!E.spill || level_first <= E.store_base) return KMC_OK;
+  const uint64_t n = level_first - E.store_base;
+  E.host_store.resize(level_first * W);
+  E.host_parent.resize(level_first);
+  int rc = copy_ring_range(E, E.store_base, n, E.host_store.data() + E.store_base * W, E.host_parent.data() + E.store_base);
+  if (rc) return rc;
+  E.store_base = level_first;
+  return KMC_OK;
+}
+
+// ---- checkpoint / recover (TLC -checkpoint / -recover): written at a level boundary -------------------------------
+// <dir>/checkpoint.meta  text: key value per line;  <dir>/checkpoint.bin  states [0, tail) then parent words [0, tail).
+// The fingerprint set is not stored: it is rebuilt from the states on recover (and may then have another size).
+struct LevelCursor {
+  uint64_t level_first, level_end, level;
+};
+static int write_checkpoint(Engine& E, const DevCounters& h, const LevelCursor& lc) {
+  const std::string meta = E.checkpoint_dir + "/checkpoint.meta", bin = E.checkpoint_dir + "/checkpoint.bin";
+  const std::string tmp = bin + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) {
+    E.last_error = "cannot write " + tmp;
+    return KMC_E_BADARG;
+  }
+  const uint64_t tail = h.store_tail;
+  std::vector<uint64_t> st((size_t)(tail - E.store_base) * W), pa((size_t)(tail - E.store_base));
+  int rc = copy_ring_range(E, E.store_base, tail - E.store_base, st.data(), pa.data());
+  if (rc) { fclose(f); return rc; }
+  bool ok = fwrite(E.host_store.data(), 8, (size_t)E.store_base * W, f) == (size_t)E.store_base * W &&
+            fwrite(st.data(), 8, st.size(), f) == st.size() &&
+            fwrite(E.host_parent.data(), 8, (size_t)E.store_base, f) == (size_t)E.store_base &&
+            fwrite(pa.data(), 8, pa.size(), f) == pa.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), bin.c_str()) != 0) {
+    E.last_error = "short write on " + tmp;
+    return KMC_E_BADARG;
+  }
+  f = fopen((meta + ".tmp").c_str(), "w");
+  if (!f) return KMC_E_BADARG;
+  fprintf(f, "model %s\ndigest %s\nwords %d\ntail %llu\nlevel_first %llu\nlevel_end %llu\nlevel %llu\ngenerated %llu\n"
+             "deadlocks %llu\nout_of_model %llu\nprobes %llu\nwidths",
+          KMC_MODEL_NAME, KMC_MODEL_DIGEST, W, (unsigned long long)tail, (unsigned long long)lc.level_first,
+          (unsigned long long)lc.level_end, (unsigned long long)lc.level, (unsigned long long)h.generated,
+          (unsigned long long)h.deadlocks, (unsigned long long)h.out_of_model, (unsigned long long)h.probes);
+  for (uint64_t w : E.widths) fprintf(f, " %llu", (unsigned long long)w);
+  fprintf(f, "\n");
+  fclose(f);
+  if (rename((meta + ".tmp").c_str(), meta.c_str()) != 0) return KMC_E_BADARG;
+  E.last_checkpoint = std::chrono::steady_clock::now();
+  return KMC_OK;
+}
+
+static int read_checkpoint(Engine& E, DevCounters* h, LevelCursor* lc) {
+  const std::string meta = E.recover_dir + "/checkpoint.meta", bin = E.recover_dir + "/checkpoint.bin";
+  FILE* f = fopen(meta.c_str(), "r");
+  if (!f) {
+    E.last_error = "cannot read " + meta;
+    return KMC_E_BADARG;
+  }
+  char key[64], val[256];
+  unsigned long long tail = 0, words = 0;
+  std::string digest;
+  memset(h, 0, sizeof(*h));
+  E.widths.clear();
+  while (fscanf(f, "%63s", key) == 1) {
+    if (!strcmp(key, "widths")) {
+      unsigned long long w;
+      while (fscanf(f, "%llu", &w) == 1) E.widths.push_back(w);
+      break;
+    }
+    if (fscanf(f, "%255s", val) != 1) break;
+    const unsigned long long v = strtoull(val, nullptr, 10);
+    if (!strcmp(key, "digest")) digest = val;
+    else if (!strcmp(key, "words")) words = v;
+    else if (!strcmp(key, "tail")) tail = v;
+    else if (!strcmp(key, "level_first")) lc->level_first = v;
+    else if (!strcmp(key, "level_end")) lc->level_end = v;
+    else if (!strcmp(key, "level")) lc->level = v;
+    else if (!strcmp(key, "generated")) h->generated = v;
+    else if (!strcmp(key, "deadlocks")) h->deadlocks = v;
+    else if (!strcmp(key, "out_of_model")) h->out_of_model = v;
+    else if (!strcmp(key, "probes")) h->probes = v;
+  }
+  fclose(f);
+  if (digest != KMC_MODEL_DIGEST || words != (unsigned long long)W) {
+    E.last_error = "checkpoint belongs to another model (digest mismatch)";
+    return KMC_E_MODEL;
+  }
+  h->store_tail = tail;
+  // states below the level to expand go to the host (spill) or, without spill, everything to the device
+  const uint64_t keep_from = E.spill ? lc->level_first : 0;
+  if (tail - keep_from > E.max_states) {
+    E.last_error = "checkpoint does not fit the state store (raise max_states or use spill)";
+    return KMC_E_STORE_FULL;
+  }
+  f = fopen(bin.c_str(), "rb");
+  if (!f) {
+    E.last_error = "cannot read " + bin;
+    return KMC_E_BADARG;
+  }
+  std::vector<uint64_t> st((size_t)tail * W), pa((size_t)tail);
+  bool ok = fread(st.data(), 8, st.size(), f) == st.size() && fread(pa.data(), 8, pa.size(), f) == pa.size();
+  fclose(f);
+  if (!ok) {
+    E.last_error = "short read on " + bin;
+    return KMC_E_BADARG;
+  }
+  E.store_base = keep_from;
+  E.host_store.assign(st.begin(), st.begin() + (size_t)keep_from * W);
+  E.host_parent.assign(pa.begin(), pa.begin() + (size_t)keep_from);
+  // device window
+  for (uint64_t g = keep_from; g < tail;) {
+    const uint64_t slot = E.spill ? (g & (E.max_states - 1)) : g;
+    const uint64_t n = E.spill ? std::min<uint64_t>(tail - g, E.max_states - slot) : tail - g;
+    CK(cudaMemcpyAsync(E.store + slot * W, st.data() + g * W, n * W * 8, cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(E.parent + slot, pa.data() + g, n * 8, cudaMemcpyHostToDevice, E.stream));
+    g += n;
+  }
+  // rebuild the set: every stored state is inserted once, in batches through the candidate buffer
+  Params p = E.params();
+  const uint64_t batch = E.region_rows * ROW / W;
+  for (uint64_t g = 0; g < tail; g += batch) {
+    const uint64_t n = std::min<uint64_t>(batch, tail - g);
+    CK(cudaMemcpyAsync(E.cand, st.data() + g * W, n * W * 8, cudaMemcpyHostToDevice, E.stream));
+    k_rebuild<<<grid_for(E, n, 256, 8), 256, 0, E.stream>>>(p, E.cand, n);
+    CK(cudaStreamSynchronize(E.stream));
+  }
+  CK(cudaMemcpyAsync(&E.ctr->store_tail, &h->store_tail, 8, cudaMemcpyHostToDevice, E.stream));
+  CK(cudaMemcpyAsync(&E.ctr->generated, &h->generated, 8, cudaMemcpyHostToDevice, E.stream));
+  CK(cudaMemcpyAsync(&E.ctr->deadlocks, &h->deadlocks, 8, cudaMemcpyHostToDevice, E.stream));
+  CK(cudaMemcpyAsync(&E.ctr->out_of_model, &h->out_of_model, 8, cudaMemcpyHostToDevice, E.stream));
+  CK(cudaMemcpyAsync(&E.ctr->probes, &h->probes, 8, cudaMemcpyHostToDevice, E.stream));
+  CK(cudaStreamSynchronize(E.stream));
+  DevCounters now;
+  int rc = read_counters(E, &now);
+  if (rc) return rc;
+  return fail_to_error(now.fail);
+}
+
 // Picks the violator with the smallest fingerprint (deadlocks, which belong to the level being
 // expanded, before invariant violations of the next level) and walks its parent links back to an
 // initial state.  `level` is the level being expanded (0 for the init insert).
@@ -1549,10 +1765,12 @@ static int build_trace(Engine& E, const DevCounters& h, uint64_t level) {
   while ((meta & 0x0000FFFFFFFFFFFFull) != NO_PARENT && guard++ < 100000) {
     uint64_t idx = meta & IDX_MASK;
     uint32_t prank = (uint32_t)((meta >> 40) & 0xFF);
-    if (prank != E.rank || idx >= E.max_states) break;  // parent lives on another rank
+    if (prank != E.rank || idx - E.store_base >= E.max_states && idx >= E.store_base) break;  // parent lives on another rank
     std::vector<uint64_t> st(W);
-    CK(cudaMemcpy(st.data(), E.store + idx * W, W * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&meta, E.parent + idx, 8, cudaMemcpyDeviceToHost));
+    {
+      int frc = fetch_state(E, idx, st.data(), &meta);
+      if (frc) return frc;
+    }
     rev.push_back(st);
     rev_act.push_back((uint32_t)(meta >> 56));
   }
@@ -1588,28 +1806,47 @@ static int engine_run(Engine& E) {
     return KMC_E_BADARG;
   }
   CK(cudaEventRecord(E.ev_begin, E.stream));
-  rc = seed_init(E);
-  if (rc) return rc;
-  rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, M::NUM_INIT);
-  if (rc) return rc;
-  if ((rc = launch_invariants(E, 0, M::NUM_INIT))) return rc;
   DevCounters h;
-  rc = read_counters(E, &h);
-  if (rc) return rc;
-  uint64_t level_first = 0, level_end = h.store_tail, level = 1;
+  uint64_t level_first = 0, level_end = 0, level = 1;
   bool stopped = false;
-  int err = fail_to_error(h.fail);
-  if (!err && h.viol_count) {
-    build_trace(E, h, 0);
-    if (!E.cont) stopped = true;
+  int err = 0;
+  E.last_checkpoint = std::chrono::steady_clock::now();
+  if (!E.recover_dir.empty()) {
+    // -recover: continue from the level boundary a checkpoint was written at
+    LevelCursor lc{0, 0, 1};
+    if ((rc = read_checkpoint(E, &h, &lc))) return rc;
+    level_first = lc.level_first;
+    level_end = lc.level_end;
+    level = lc.level;
+  } else {
+    rc = seed_init(E);
+    if (rc) return rc;
+    rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, M::NUM_INIT);
+    if (rc) return rc;
+    if ((rc = launch_invariants(E, 0, M::NUM_INIT))) return rc;
+    rc = read_counters(E, &h);
+    if (rc) return rc;
+    level_end = h.store_tail;
+    err = fail_to_error(h.fail);
+    if (!err && h.viol_count) {
+      build_trace(E, h, 0);
+      if (!E.cont) stopped = true;
+    }
   }
   while (!err && !stopped && level_end > level_first) {
     E.widths.push_back(level_end - level_first);
+    if ((rc = spill_below(E, level_first))) return rc;         // (no-op unless spilling)
+    // a chunk never crosses the wrap of the ring store
+    auto chunk_len = [&](uint64_t off) {
+      uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+      if (E.spill) cnt = std::min<uint64_t>(cnt, E.max_states - (off & (E.max_states - 1)));
+      return cnt;
+    };
     if (E.overlap) {
       // K1 of chunk i+1 (stream) overlaps K2 of chunk i (stream2); the two halves of the candidate buffer alternate
       uint32_t slot = 0;
-      for (uint64_t off = level_first; off < level_end; off += E.chunk_states, slot ^= 1) {
-        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+      for (uint64_t off = level_first, cnt; off < level_end; off += cnt, slot ^= 1) {
+        cnt = chunk_len(off);
         CK(cudaStreamWaitEvent(E.stream, E.ev_ins[slot], 0));            // the K2 that read this half has finished
         CK(cudaMemsetAsync(&E.ctr->cand_count[slot], 0, sizeof(unsigned long long), E.stream));
         if ((rc = launch_expand(E, off, cnt, false, slot))) return rc;
@@ -1622,8 +1859,8 @@ static int engine_run(Engine& E) {
       CK(cudaStreamWaitEvent(E.stream, E.ev_ins[0], 0));
       CK(cudaStreamWaitEvent(E.stream, E.ev_ins[1], 0));
     } else {
-      for (uint64_t off = level_first; off < level_end; off += E.chunk_states) {
-        uint64_t cnt = std::min<uint64_t>(E.chunk_states, level_end - off);
+      for (uint64_t off = level_first, cnt; off < level_end; off += cnt) {
+        cnt = chunk_len(off);
         if ((rc = reset_cand(E))) return rc;
         if ((rc = launch_expand(E, off, cnt))) return rc;
         if ((rc = launch_insert(E, E.cand, &E.ctr->cand_count[0], 0, cnt * (uint64_t)E.fanout_bound))) return rc;
@@ -1634,7 +1871,7 @@ static int engine_run(Engine& E) {
     err = fail_to_error(h.fail);
     {
       std::lock_guard<std::mutex> g(E.mu);
-      E.stats.distinct = std::min<uint64_t>(h.store_tail, E.max_states);
+      E.stats.distinct = E.spill ? h.store_tail : std::min<uint64_t>(h.store_tail, E.max_states);
       E.stats.generated = h.generated;
       E.stats.depth = level;
       E.stats.queue = h.store_tail - level_end;
@@ -1651,6 +1888,13 @@ static int engine_run(Engine& E) {
     level_first = level_end;
     level_end = h.store_tail;
     ++level;
+    if (!err && !E.checkpoint_dir.empty() && level_end > level_first) {
+      const double mins = std::chrono::duration<double>(std::chrono::steady_clock::now() - E.last_checkpoint).count() / 60.0;
+      if (mins >= E.checkpoint_minutes) {
+        if ((rc = spill_below(E, level_first))) return rc;
+        if ((rc = write_checkpoint(E, h, LevelCursor{level_first, level_end, level}))) return rc;
+      }
+    }
     if (E.stop_after_states && h.store_tail >= E.stop_after_states && level_end > level_first) {
       stopped = true;          // bounded throughput run: the queue is reported, no error
       break;
@@ -1664,7 +1908,7 @@ static int engine_run(Engine& E) {
   {
     std::lock_guard<std::mutex> g(E.mu);
     kmc_stats_t& st = E.stats;
-    st.distinct = std::min<uint64_t>(h.store_tail, E.max_states);
+    st.distinct = E.spill ? h.store_tail : std::min<uint64_t>(h.store_tail, E.max_states);
     st.generated = h.generated;
     st.queue = stopped ? (level_end - level_first) : 0;
     st.depth = E.widths.size();
@@ -1714,6 +1958,10 @@ int kmcm_create(const char* options_json, kmcm_ctx** out) {
   if (json_bool(options_json, "one_phase", &b)) E.one_phase = b;
   if (json_bool(options_json, "prefetch", &b)) E.prefetch = b;
   if (json_bool(options_json, "overlap", &b)) E.overlap = b;
+  if (json_bool(options_json, "spill", &b)) E.spill = b;
+  json_str(options_json, "checkpoint_dir", &E.checkpoint_dir);
+  json_str(options_json, "recover", &E.recover_dir);
+  if (json_num(options_json, "checkpoint_minutes", &d)) E.checkpoint_minutes = d;
   if (json_num(options_json, "chunk_states", &d)) E.chunk_states_opt = (uint64_t)d;
   if (json_num(options_json, "fanout_bound", &d)) E.fanout_bound = (uint32_t)d;
   if (json_num(options_json, "stream", &d) && d != 0) {
@@ -1841,8 +2089,16 @@ int kmcm_copy_parents(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64
   kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
   if (!c || !buf) return KMC_E_BADARG;
   if (!c->ranks.empty()) return KMC_E_STATE;      // per-rank stores: address a rank's own context
-  if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaSetDevice(E.device));
+  if (E.spill) {
+    std::vector<uint64_t> tmp(W);
+    for (uint64_t i = 0; i < count; ++i) {
+      int rc = fetch_state(E, first + i, tmp.data(), buf + i);
+      if (rc) return rc;
+    }
+    return KMC_OK;
+  }
+  if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaMemcpy(buf, E.parent + first, count * 8, cudaMemcpyDeviceToHost));
   return KMC_OK;
 }
@@ -1851,8 +2107,16 @@ int kmcm_copy_states(const kmcm_ctx* c_, uint64_t first, uint64_t count, uint64_
   kmcm_ctx* c = const_cast<kmcm_ctx*>(c_);
   if (!c || !buf) return KMC_E_BADARG;
   if (!c->ranks.empty()) return KMC_E_STATE;
-  if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaSetDevice(E.device));
+  if (E.spill) {
+    uint64_t meta;
+    for (uint64_t i = 0; i < count; ++i) {
+      int rc = fetch_state(E, first + i, buf + i * W, &meta);
+      if (rc) return rc;
+    }
+    return KMC_OK;
+  }
+  if (first + count > E.max_states) return KMC_E_BADARG;
   CK(cudaMemcpy(buf, E.store + first * W, count * W * 8, cudaMemcpyDeviceToHost));
   return KMC_OK;
 }

@@ -1,7 +1,8 @@
 """``tlc2.TLC``-compatible command line on top of the C ABI.
 
     python -m kafka_specification_b200.tlc2 [-config F.cfg] [-workers N|auto] [-deadlock] [-continue]
-                                             [-fpbits N] [-maxstates N] [-I dir] [-metadir d] [-tool] SPEC
+                                             [-fpbits N] [-maxstates N] [-I dir] [-metadir d] [-checkpoint MIN]
+                                             [-recover DIR] [-spill] [-tool] SPEC
 
 ``SPEC`` is a module name or a path to ``SPEC.tla``; modules it EXTENDS / INSTANCEs are resolved
 from the same directory (and ``-I`` directories), like TLC does.  The spec and its ``.cfg`` are
@@ -43,7 +44,11 @@ def parse_args(argv):
     ap.add_argument("-fpbits", type=int, default=0, help="log2 of the fingerprint-set slots")
     ap.add_argument("-maxstates", type=int, default=0)
     ap.add_argument("-I", action="append", default=[])
-    ap.add_argument("-metadir")
+    ap.add_argument("-metadir", help="directory for checkpoints (TLC: states/<timestamp>)")
+    ap.add_argument("-checkpoint", type=float, default=None, help="minutes between checkpoints (TLC default 30; 0 = every level)")
+    ap.add_argument("-recover", help="resume from the checkpoint in this directory")
+    ap.add_argument("-spill", action="store_true",
+                    help="extension: keep only the live BFS window in HBM and move older levels to host memory")
     ap.add_argument("-tool", action="store_true")
     ap.add_argument("-device", type=int, default=0)
     ap.add_argument("-cleanup", action="store_true")
@@ -127,9 +132,9 @@ def main(argv=None) -> int:
         msg("general", f"Error: {e}", 1)
         return EXIT_ERROR_SPEC
     except LowerError as e:
-        msg = str(e)
-        msg("general", f"Error: {msg}", 1)
-        return EXIT_VIOLATION_ASSUMPTION if "ASSUME" in msg else EXIT_ERROR_SPEC
+        text = str(e)
+        msg("general", f"Error: {text}", 1)
+        return EXIT_VIOLATION_ASSUMPTION if "ASSUME" in text else EXIT_ERROR_SPEC
     msg("starting", f"Starting... ({time.strftime('%Y-%m-%d %H:%M:%S')})")
     opts = {"device": a.device}
     if n_gpus > 1:
@@ -142,6 +147,15 @@ def main(argv=None) -> int:
         opts["cont"] = True
     if a.deadlock:
         opts["check_deadlock"] = False
+    if a.metadir or a.checkpoint is not None:
+        ckdir = a.metadir or os.path.join("states", time.strftime("%y-%m-%d-%H-%M-%S"))
+        os.makedirs(ckdir, exist_ok=True)
+        opts["checkpoint_dir"] = ckdir
+        opts["checkpoint_minutes"] = 30.0 if a.checkpoint is None else a.checkpoint
+    if a.recover:
+        opts["recover"] = a.recover
+    if a.spill:
+        opts["spill"] = True
     try:
         ck = Checker(name, **opts)
     except KmcError as e:

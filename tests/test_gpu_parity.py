@@ -252,6 +252,58 @@ def test_headline_sizes_match_oracle_b_golden(name, opts, goldens):
     assert r.levels == g["levels"]
 
 
+def test_spill_store_smaller_than_the_state_space(goldens):
+    """spill: the device store is a ring over the live window (the level being expanded + the one being built);
+    older levels move to host memory.  262,144 slots for 737,794 states: identical counts and widths."""
+    g = goldens["kip320_small"]
+    with checker("kip320_small", spill=True, max_states=1 << 18, cont=True) as ck:
+        r = ck.run()
+        assert r.stats["max_states"] == 1 << 18
+        # every state is still addressable (host spill + device ring) and decodes to a distinct value
+        rows = ck.copy_states(0, 5000)
+        assert len({tuple(int(x) for x in row) for row in rows}) == 5000
+    assert r.complete and (r.distinct, r.generated, r.depth, r.deadlocks, r.levels) == (
+        g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+    # without spill the same store is too small
+    from kafka_specification_b200.runtime import KmcError
+    with checker("kip320_small", max_states=1 << 18) as ck:
+        with pytest.raises(KmcError) as e:
+            ck.run()
+        assert e.value.code == -5
+
+
+def test_error_trace_through_spilled_levels(goldens):
+    """The parent links of a counterexample reach back into levels that were spilled to the host."""
+    g = goldens["trunchw_small"]
+    first = min(l for l in g["first_violation_level"].values() if l)
+    with checker("trunchw_small", spill=True, max_states=1 << 14) as ck:
+        r = ck.run()
+        assert not r.complete and r.violation["level"] == first and len(r.trace) == first
+        _assert_trace_is_behaviour("trunchw_small", r.trace, ck)
+
+
+def test_checkpoint_and_recover(tmp_path, goldens):
+    """-checkpoint / -recover: a run that stops (here: bounded) leaves a checkpoint at a level boundary; a new context
+    recovers it (the set is rebuilt from the stored states) and finishes with the golden's counts and widths."""
+    g = goldens["kip320_small"]
+    d = str(tmp_path)
+    with checker("kip320_small", checkpoint_dir=d, stop_after_states=200_000) as ck:
+        a = ck.run()
+    assert not a.complete and a.queue > 0
+    assert os.path.exists(os.path.join(d, "checkpoint.meta")) and os.path.exists(os.path.join(d, "checkpoint.bin"))
+    for extra in ({}, {"spill": True, "max_states": 1 << 18}):
+        with checker("kip320_small", recover=d, cont=True, **extra) as ck:
+            b = ck.run()
+        assert b.complete and (b.distinct, b.generated, b.depth, b.deadlocks, b.levels) == (
+            g["distinct"], g["generated"], g["depth"], g["deadlocks"], g["levels"])
+    # a checkpoint of another model is refused
+    from kafka_specification_b200.runtime import KmcError
+    with checker("kip279_small", recover=d) as ck:
+        with pytest.raises(KmcError) as e:
+            ck.run()
+        assert e.value.code == -7
+
+
 def test_bounded_run_stops_cleanly():
     """stop_after_states: a bounded throughput run ends at a level boundary with the queue reported."""
     with checker("kip320_small", stop_after_states=100_000) as ck:
