@@ -55,7 +55,6 @@ def parse_args(argv):
     ap.add_argument("-nowarning", action="store_true")
     ap.add_argument("-fp", type=int, default=0)
     ap.add_argument("-fpmem", type=float, default=0)
-    ap.add_argument("-checkpoint", type=int, default=0)
     ap.add_argument("-coverage", type=int, default=0)
     ap.add_argument("spec")
     return ap.parse_args(argv)

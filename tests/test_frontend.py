@@ -132,6 +132,6 @@ def test_models_directory_cfgs_parse():
     for f in os.listdir(d):
         if f.endswith(".cfg"):
             cfg = parse_cfg(open(os.path.join(d, f)).read())
-            assert cfg.init == "Init" and cfg.next == "Next"
+            assert cfg.init == "Init" and cfg.next in ("Next", "NextWith279")     # (MCKip320With279: the reference's proposed experiment)
             n += 1
     assert n >= 10
