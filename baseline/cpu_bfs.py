@@ -22,7 +22,15 @@ def build(model: str) -> str:
     src = os.path.join(HERE, "cpu_bfs.cpp")
     if not os.path.exists(hdr):
         raise RuntimeError(f"{hdr} is missing: build the model first")
-    tag = hashlib.sha256(open(hdr, "rb").read() + open(src, "rb").read()).hexdigest()[:12]
+    # -march=native: the cache key includes this machine's CPU flags, so a library built on the build host is never
+    # reused on the GPU box (another CPU => illegal instruction)
+    cpu = b""
+    try:
+        with open("/proc/cpuinfo", "rb") as f:
+            cpu = next((l for l in f if l.startswith(b"flags")), b"")
+    except OSError:
+        pass
+    tag = hashlib.sha256(open(hdr, "rb").read() + open(src, "rb").read() + cpu).hexdigest()[:12]
     os.makedirs(OUT, exist_ok=True)
     so = os.path.join(OUT, f"cpu_{model}_{tag}.so")
     if not os.path.exists(so):

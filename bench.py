@@ -303,7 +303,7 @@ def run_single(args):
     # of the same size (tools/gather_bench.cu -> profiles/gather_peak.json)
     gp = os.path.join(ROOT, "profiles", "gather_peak.json")
     if os.path.exists(gp) and ins_ms > 0:
-        want = res.stats["table_slots"] * 8
+        want = res.stats["table_slots"] * (res.stats.get("slot_bytes") or 8)
         pts = load_json(gp)["results"]
         best = min(pts, key=lambda r: abs(r["table_bytes"] - want))
         probes_per_s = steps * res.stats["probes"] / (ins_ms / 1000.0)
@@ -313,8 +313,19 @@ def run_single(args):
     r_inv = roof("k_invariants", inv_bytes, inv_ms, n_inv)
     ranked = sorted([r_exp, r_ins, r_inv], key=lambda r: -r["share_of_gpu_time"])
     dominant, other = ranked[0], ranked[1:]
-    cpu = cpu_run(args.model) if not args.no_cpu_baseline else None
-    cold = cold_start(args.model, opts) if not args.no_cold else None
+    # the auxiliary legs must never cost the headline line: a failure there is reported in place of the number
+    cpu = cold = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_run(args.model)
+        except BaseException as e:                       # (cpu_run raises SystemExit on a parity failure)
+            cpu = {"value": None, "unit": "states/s", "cores": os.cpu_count(), "kind": "port", "same_config": False,
+                   "sample": f"cpu baseline failed: {e!r}"[:300]}
+    if not args.no_cold:
+        try:
+            cold = cold_start(args.model, opts)
+        except BaseException as e:
+            cold = {"seconds": None, "error": repr(e)[:300]}
     info = ck.info
     depth = res.depth
     line = {
