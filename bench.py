@@ -367,7 +367,39 @@ def run_sharded(args):
         opts["p2p"] = False
     eng = CudaShardEngine(args.model, rank, world, local, **opts)
     drv = ShardedChecker(eng)
-    for _ in range(args.warmup):
+    g = golden_for(args.model)
+    sync_note = None
+
+    def agreed_run():
+        """One run on every rank; all ranks learn whether it succeeded everywhere and matched the golden."""
+        r, err = None, None
+        try:
+            r = drv.run()
+            if g and (r.distinct, r.generated, r.depth, r.levels) != (g["distinct"], g["generated"], g["depth"], g["levels"]):
+                err = f"result differs from the golden: {(r.distinct, r.generated, r.depth)}"
+        except Exception as ex:                       # KmcError (incl. KMC_E_PEER_TIMEOUT), RuntimeError
+            err = repr(ex)[:200]
+        ok = torch.tensor([0 if err else 1], dtype=torch.int64, device=eng.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return r, err, bool(ok.item())
+
+    # The first warm-up run doubles as the acceptance run of the device-side round/level synchronisation (flags in
+    # peer memory): if it fails on any rank, every rank falls back to the stream-ordered NCCL barrier per round (the
+    # exchange itself stays fused) -- and the line says so.
+    if args.warmup > 0 and eng.p2p and eng.device_sync:
+        _, err, ok = agreed_run()
+        if not ok:
+            errs = [None] * world
+            dist.all_gather_object(errs, err)
+            sync_note = "device-side sync failed in the first warm-up run, NCCL barrier per round used instead: " + \
+                        "; ".join(f"rank {i}: {e}" for i, e in enumerate(errs) if e)
+            if rank == 0:
+                print("[bench] " + sync_note, file=sys.stderr, flush=True)
+            eng.device_sync = False
+        n_warm = args.warmup - 1
+    else:
+        n_warm = args.warmup
+    for _ in range(n_warm):
         drv.run()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -415,6 +447,11 @@ def run_sharded(args):
                                               "parity": parity, "parallelism": f"fingerprint-sharded x{world}",
                                               "exchange": "fused: expand kernel stores rows into the owners' inboxes over NVLink (CUDA IPC)"
                                               if eng.p2p else "NCCL all-to-all-v per chunk",
+                                              "round_sync": ("device-side flags in peer memory, one host sync per level"
+                                                             if (eng.p2p and eng.device_sync) else
+                                                             "stream-ordered NCCL barrier per round, host read-back per level"),
+                                              "round_sync_note": sync_note,
+                                              "nvlink_bytes_per_step_est": int(G * (world - 1) / world * (W + 1) * 8),
                                               "per_rank_distinct": res.per_rank_distinct,
                                               "exchanged_rows_per_step": res.exchanged_rows}),
             "roofline": {"kernel": "k_insert (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -51,7 +51,8 @@ enum {
   KMC_E_MODEL = -7,           /* cannot load / mismatching lowered model library         */
   KMC_E_STATE = -8,           /* call sequence error (e.g. trace before run)             */
   KMC_E_NO_GPU = -9,          /* no CUDA device: there is deliberately no CPU fallback   */
-  KMC_E_CAND_FULL = -10       /* candidate buffer overflow (raise cand_bytes / fanout_bound) */
+  KMC_E_CAND_FULL = -10,      /* candidate buffer overflow (raise cand_bytes / fanout_bound) */
+  KMC_E_PEER_TIMEOUT = -11    /* multi-GPU: a peer rank never reached a device-side synchronisation point */
 };
 
 /* result kinds (kmc_violation_t.kind); a driver maps them to TLC's exit codes 0/12/11 */

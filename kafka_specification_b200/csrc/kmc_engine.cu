@@ -60,6 +60,7 @@ static_assert(M::NUM_ACTIONS <= 255, "the parent word holds the action id in 8 b
 #define KMC_FAIL_TABLE_FULL 2
 #define KMC_FAIL_STORE_FULL 3
 #define KMC_FAIL_CAND_FULL 4
+#define KMC_FAIL_PEER_TIMEOUT 5
 
 // ----------------------------------------------------------------------------------------
 // fingerprints
@@ -996,17 +997,35 @@ __global__ void k_publish_counts(Params p, uint64_t round) {
   }
 }
 
-// Device-side wait (one warp): lane i spins until flags[i] >= value.  The flags live in this rank's own memory
-// (peers push), so the polling never crosses NVLink.
-__global__ void k_wait_flags(const uint64_t* flags, unsigned n, uint64_t value) {
-  unsigned i = threadIdx.x;
-  if (i < n) {
-    unsigned ns = 32;
-    while (ld_acquire_sys(flags + i) < value) {
-      __nanosleep(ns);
-      if (ns < 1024) ns <<= 1;
+// A device-side wait is bounded: a peer that never arrives (its process died, its context failed) turns into
+// KMC_E_PEER_TIMEOUT on this rank after PEER_TIMEOUT_NS instead of a kernel that spins for ever and takes the
+// GPU with it.  Once the flag is up, later waits of the run return at once (the run is lost anyway).
+static constexpr unsigned long long PEER_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag(const uint64_t* flag, uint64_t value, DevCounters* ctr) {
+  if (ld_acquire_sys(flag) >= value) return;
+  if (*(volatile unsigned long long*)&ctr->fail == KMC_FAIL_PEER_TIMEOUT) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned ns = 32;
+  while (ld_acquire_sys(flag) < value) {
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+    if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) {
+      atomicCAS(&ctr->fail, 0ull, (unsigned long long)KMC_FAIL_PEER_TIMEOUT);
+      return;
     }
   }
+}
+
+// Device-side wait (one warp): lane i waits until flags[i] >= value.  The flags live in this rank's own memory
+// (peers push), so the polling never crosses NVLink.
+__global__ void k_wait_flags(const uint64_t* flags, unsigned n, uint64_t value, DevCounters* ctr) {
+  unsigned i = threadIdx.x;
+  if (i < n) wait_flag(flags + i, value, ctr);
 }
 
 // after the insert of a round: every source may now reuse this rank's inbox buffer of that round
@@ -1040,12 +1059,13 @@ __global__ void k_gather_level(Params p, uint64_t level_id, uint64_t* host_out) 
   unsigned r = threadIdx.x;
   const uint64_t* board = sync_page(p, p.rank) + SYNC_BOARD;
   if (r < p.world) {
-    unsigned ns = 32;
-    while (ld_acquire_sys(board + r * BOARD_WORDS) < level_id) {
-      __nanosleep(ns);
-      if (ns < 1024) ns <<= 1;
-    }
+    wait_flag(board + r * BOARD_WORDS, level_id, p.ctr);
     for (int k = 0; k < BOARD_WORDS; ++k) host_out[r * BOARD_WORDS + k] = board[r * BOARD_WORDS + k];
+    // a timed-out wait of this level (or of one of its rounds) reaches the host through this rank's own entry
+    if (r == p.rank) {
+      const unsigned long long f = *(volatile unsigned long long*)&p.ctr->fail;
+      if (f == KMC_FAIL_PEER_TIMEOUT) host_out[r * BOARD_WORDS + 5] = f;
+    }
   }
 }
 
@@ -1484,6 +1504,7 @@ static int fail_to_error(unsigned long long f) {
     case KMC_FAIL_TABLE_FULL: return KMC_E_TABLE_FULL;
     case KMC_FAIL_STORE_FULL: return KMC_E_STORE_FULL;
     case KMC_FAIL_CAND_FULL: return KMC_E_CAND_FULL;
+    case KMC_FAIL_PEER_TIMEOUT: return KMC_E_PEER_TIMEOUT;
     default: return KMC_E_CUDA;
   }
 }
@@ -2134,6 +2155,7 @@ const char* kmcm_strerror(const kmcm_ctx* c, int code) {
     case KMC_E_STATE: return "call sequence error";
     case KMC_E_NO_GPU: return "no CUDA device visible; this library has no CPU fallback";
     case KMC_E_CAND_FULL: return "candidate buffer overflow (raise cand_bytes or fanout_bound)";
+    case KMC_E_PEER_TIMEOUT: return "a peer rank did not arrive at a device-side synchronisation point within 30 s";
     default: return "unknown error";
   }
 }
@@ -2374,7 +2396,7 @@ int kmcm_shard_round_p2p(kmcm_ctx* c, uint64_t first, uint64_t count, int seed) 
   const uint64_t round = ++E.round;
   E.inbox_buf = (uint32_t)(round & 1);
   int rc;
-  if (round > 2) k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_DONE, E.world, round - 2);
+  if (round > 2) k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_DONE, E.world, round - 2, E.ctr);
   if (seed) {
     if ((rc = seed_p2p(c, false))) return rc;
   } else {
@@ -2384,7 +2406,7 @@ int kmcm_shard_round_p2p(kmcm_ctx* c, uint64_t first, uint64_t count, int seed) 
   Params p = E.params();
   p.p2p = 1;
   k_publish_counts<<<1, 32, 0, E.stream>>>(p, round);
-  k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_READY, E.world, round);
+  k_wait_flags<<<1, 32, 0, E.stream>>>(E.inbox_alloc + SYNC_READY, E.world, round, E.ctr);
   {
     TimedLaunch t(E, 1);
     k_insert_inbox<<<E.sms * 8, 256, 0, E.stream>>>(p);

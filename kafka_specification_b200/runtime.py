@@ -22,7 +22,7 @@ BUILD = os.path.join(ROOT, "build")
 KMC_ERRORS = {
     0: "KMC_OK", -1: "KMC_E_BADARG", -2: "KMC_E_CUDA", -3: "KMC_E_OOM", -4: "KMC_E_TABLE_FULL",
     -5: "KMC_E_STORE_FULL", -6: "KMC_E_LAYOUT_OVERFLOW", -7: "KMC_E_MODEL", -8: "KMC_E_STATE", -9: "KMC_E_NO_GPU",
-    -10: "KMC_E_CAND_FULL",
+    -10: "KMC_E_CAND_FULL", -11: "KMC_E_PEER_TIMEOUT",
 }
 
 

@@ -358,7 +358,9 @@ class ShardedChecker:
         return ShardedResult(distinct=sum(r[0] for r in rows), generated=sum(r[1] for r in rows), depth=len(levels),
                              deadlocks=sum(r[2] for r in rows), levels=levels, complete=not stopped,
                              violation=viol, per_rank_distinct=[r[0] for r in rows], seconds=seconds,
-                             exchanged_rows=sum(r[1] for r in rows), stats=st, trace=trace)
+                             # rows that crossed NVLink: no counter on the fused path (the rows leave inside K1's
+                             # flush); with the uniform owner hash it is generated * (world - 1) / world
+                             exchanged_rows=sum(r[1] for r in rows) * (self.world - 1) // self.world, stats=st, trace=trace)
 
     def _run(self) -> ShardedResult:
         e = self.e
