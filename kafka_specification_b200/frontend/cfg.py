@@ -16,6 +16,8 @@ valid TLC configuration:
 
     \\* kspec: LAYOUT LayoutOk                    operator whose conjuncts give each variable's type
     \\* kspec: CAPACITY leaderAndIsrRequests = MaxLeaderEpoch + 1
+                                                  bound on the cardinality of a set variable stored as a sorted array, or
+                                                  on the length of a `v \\in Seq(S)` variable (checked: a longer value traps)
     \\* kspec: TYPE leaderAndIsrRequests \\subseteq [leaderEpoch : 0 .. MaxLeaderEpoch, ...]
                                                   layout type of one variable, overriding the one inferred from the
                                                   type invariant (a checked hint: a value outside it traps)

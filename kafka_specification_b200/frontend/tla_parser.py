@@ -74,7 +74,8 @@ _BINOPS = {
     "\\union": (8, "L"), "\\intersect": (8, "L"), "\\": (8, "L"),
     "..": (9, "N"),
     "+": (10, "L"), "-": (11, "L"),
-    "*": (13, "L"), "\\div": (13, "L"),
+    "\\X": (12, "L"),                      # n-ary: A \X B \X C is the set of triples
+    "*": (13, "L"), "\\div": (13, "L"), "\\o": (13, "L"),
 }
 
 _UNIT_STARTERS = {"CONSTANT", "CONSTANTS", "VARIABLE", "VARIABLES", "ASSUME", "ASSUMPTION",
@@ -181,6 +182,21 @@ class Parser:
             mod.theorems.append(self.parse_expr())
         elif t.kind == "kw" and t.text == "INSTANCE":
             mod.instances.append(self.parse_instance(None, local))
+        elif t.kind == "kw" and t.text == "RECURSIVE":
+            # RECURSIVE Op(_, _), Op2(_): forward declarations; definitions are looked up by name when called,
+            # so nothing needs recording
+            self.advance()
+            while True:
+                self.expect_id()
+                if self.is_op("("):
+                    self.advance()
+                    while not self.is_op(")"):
+                        self.advance()
+                    self.expect_op(")")
+                if self.is_op(","):
+                    self.advance()
+                    continue
+                break
         elif t.kind == "id":
             self.parse_definition(mod, local)
         else:
@@ -256,7 +272,10 @@ class Parser:
                     op = "<="
                 if op == "/=":
                     op = "#"
-                lhs = ("binop", op, lhs, rhs)
+                if op == "\\X":
+                    lhs = ("cross", (lhs[1] if lhs[0] == "cross" else [lhs]) + [rhs])
+                else:
+                    lhs = ("binop", op, lhs, rhs)
 
     def parse_junction_list(self) -> tuple:
         bullet = self.tok

@@ -26,7 +26,7 @@ from ..frontend.modules import ModuleContext
 from ..frontend.tla_parser import Def
 from ..frontend.values import FnVal, fmt, sort_key
 from . import layout as L
-from .svals import (SYMBOLIC, LowerError, SAtom, SBool, SFn, SInt, SLazy, SRec, SSet, SUnion,
+from .svals import (SYMBOLIC, LowerError, SAtom, SBool, SFn, SInt, SLazy, SRec, SSeq, SSet, SUnion,
                     is_atom_const, is_const, is_int_const, is_static, kind_sig)
 
 
@@ -425,9 +425,7 @@ class Lowerer:
         if ka == "set":
             return self.b_and([self.subseteq(a, b), self.subseteq(b, a)])
         if ka == "tuple":
-            if len(a) != len(b):
-                return False
-            return self.b_and([self.eq(x, y) for x, y in zip(a, b)])
+            return self.seq_eq(a, b)
         raise LowerError(f"cannot compare {a!r} and {b!r}")
 
     def rec_fields(self, v) -> dict:
@@ -494,7 +492,7 @@ class Lowerer:
             return SSet([(self.b_and([c, g]), x) for g, x in self.set_items(a)] +
                         [(self.b_and([nc, g]), x) for g, x in self.set_items(b)])
         if ka == "tuple":
-            return tuple(self.mux(c, x, y) for x, y in zip(a, b))
+            return self.seq_mux(c, a, b)
         raise LowerError(f"cannot merge {a!r} and {b!r}")
 
     def union_merge(self, c, a, b):
@@ -561,6 +559,14 @@ class Lowerer:
             if len(rng) ** len(dom) > 100000:
                 raise LowerError("function set too large to enumerate")
             return [FnVal(dict(zip(dom, combo))) for combo in itertools.product(rng, repeat=len(dom))]
+        if s.kind == "cross":
+            cols = []
+            for part in s.a:
+                items = self.set_items(part)
+                if any(g is not True or not is_const(x) for g, x in items):
+                    raise LowerError("cannot enumerate a Cartesian product with state-dependent components")
+                cols.append([x for _, x in items])
+            return [tuple(combo) for combo in itertools.product(*cols)]
         raise LowerError(f"cannot enumerate {s!r}")
 
     def distinct_items(self, s):
@@ -624,6 +630,21 @@ class Lowerer:
             return self.b_and([self.b_or([self.b_not(g), self.member(e, s.a)]) for g, e in self.set_items(x)])
         if s.kind == "union":
             return self.b_or([self.member(x, s.a), self.member(x, s.b)])
+        if s.kind == "seq":
+            if k != "tuple":
+                return False
+            n, items = self.seq_parts(x)
+            if is_int_const(n):
+                return self.b_and([self.member(items[j], s.a) for j in range(n)])
+            return self.b_and([self.b_or([self.cmp("<=", n, j), self.member(items[j], s.a)]) for j in range(len(items))])
+        if s.kind == "cross":
+            if k != "tuple":
+                return False
+            n, items = self.seq_parts(x)
+            right_len = self.eq(n, len(s.a))
+            if right_len is False or len(items) < len(s.a):
+                return False
+            return self.b_and([right_len] + [self.member(items[j], part) for j, part in enumerate(s.a)])
         raise LowerError(f"membership in {s!r}")
 
     def subseteq(self, a, b):
@@ -634,6 +655,169 @@ class Lowerer:
             return frozenset(range(a, b + 1))
         A, B = self.as_sint(a), self.as_sint(b)
         return SSet([(self.b_and([self.cmp("<=", a, k), self.cmp("<=", k, b)]), k) for k in range(A.lo, B.hi + 1)])
+
+    # ------------------------------------------------------------ sequences / tuples (module Sequences)
+    # A sequence is a Python tuple when every part of it is constant, else an SSeq: a length (int or SInt) and
+    # cap item values of which the first `length` are meaningful.  Where TLC would report an error (Head / Tail of
+    # the empty sequence, an index outside 1..Len) the lowered code computes an unspecified value of the right kind.
+    def seq_parts(self, v):
+        if isinstance(v, SUnion):
+            v = self.narrow_union(v, "tuple")
+        if isinstance(v, tuple):
+            return len(v), list(v)
+        if isinstance(v, SSeq):
+            return v.n, v.items
+        raise LowerError(f"not a sequence: {v!r}")
+
+    def mk_seq(self, n, items):
+        if is_int_const(n):
+            if n < 0 or n > len(items):
+                raise LowerError("internal: sequence length outside its items")
+            items = list(items[:n])
+            return tuple(items) if all(is_const(x) for x in items) else SSeq(n, items)
+        if n.hi <= 0:
+            return ()
+        items = list(items[:n.hi])
+        if len(items) < n.hi:
+            raise LowerError("internal: sequence length bound exceeds its items")
+        return SSeq(n, items)
+
+    def int_add(self, a, k: int):
+        if is_int_const(a):
+            return a + k
+        A = self.as_sint(a)
+        return self.mk_int(f"({A.s} + {k})" if k >= 0 else f"({A.s} - {-k})", A.lo + k, A.hi + k)
+
+    def seq_at(self, v, idx):
+        n, items = self.seq_parts(v)
+        if isinstance(idx, SUnion):
+            idx = self.narrow_union(idx, "int")
+        if is_int_const(idx):
+            if not 1 <= idx <= len(items):
+                raise LowerError(f"sequence index {idx} outside 1..{len(items)}")
+            return items[idx - 1]
+        if not items:
+            raise LowerError("indexing a sequence that is always empty")
+        return self.fn_apply(SFn(list(range(1, len(items) + 1)), items), idx)
+
+    def seq_tail(self, v):
+        n, items = self.seq_parts(v)
+        if is_int_const(n):
+            if n == 0:
+                raise LowerError("Tail of the empty sequence")
+            return self.mk_seq(n - 1, items[1:])
+        A = self.as_sint(n)
+        return self.mk_seq(self.mk_int(f"({A.s} - 1)", max(A.lo - 1, 0), A.hi - 1), items[1:])
+
+    def seq_append(self, v, e):
+        n, items = self.seq_parts(v)
+        if is_int_const(n):
+            return self.mk_seq(n + 1, list(items[:n]) + [e])
+        new = []
+        for j, old in enumerate(items):
+            c = self.eq(n, j)
+            new.append(old if c is False else self.mux(c, e, old))
+        new.append(e)
+        return self.mk_seq(self.int_add(n, 1), new)
+
+    def seq_concat(self, a, b):
+        na, ia = self.seq_parts(a)
+        nb, ib = self.seq_parts(b)
+        if is_int_const(na):
+            return self.mk_seq(self.int_add(nb, na) if not is_int_const(nb) else na + nb, list(ia[:na]) + list(ib))
+        A = self.as_sint(na)
+        out = []
+        for j in range(len(ia) + len(ib)):
+            opts = []
+            if j < len(ia):
+                opts.append((self.cmp(">", na, j), ia[j]))
+            for alen in range(A.lo, min(A.hi, j) + 1):
+                if 0 <= j - alen < len(ib):
+                    opts.append((self.eq(na, alen), ib[j - alen]))
+            opts = [(c, x) for c, x in opts if c is not False]
+            if not opts:
+                break
+            val = opts[-1][1]
+            for c, x in reversed(opts[:-1]):
+                val = self.mux(c, x, val)
+            out.append(val)
+        B = self.as_sint(nb)
+        total = self.mk_int(f"({A.s} + {B.s})", A.lo + B.lo, min(A.hi + B.hi, len(out)))
+        return self.mk_seq(total, out)
+
+    def seq_subseq(self, v, m, k):
+        n, items = self.seq_parts(v)
+        if is_int_const(m) and is_int_const(k):
+            if k < m:
+                return ()
+            if m < 1 or k > len(items):
+                raise LowerError(f"SubSeq bounds {m}..{k} outside 1..{len(items)}")
+            return self.mk_seq(k - m + 1, items[m - 1:k])
+        M, K = self.as_sint(m), self.as_sint(k)
+        hi = min(K.hi, len(items)) - M.lo + 1
+        if hi <= 0:
+            return ()
+        out = [self.seq_at(v, self.int_add(m, j)) for j in range(hi) if M.lo + j <= len(items)]
+        length = self.mk_int(f"(({K.s}) >= ({M.s}) ? ({K.s}) - ({M.s}) + 1 : 0)", max(0, K.lo - M.hi + 1), len(out))
+        return self.mk_seq(length, out)
+
+    def seq_domain(self, v):
+        n, items = self.seq_parts(v)
+        if is_int_const(n):
+            return frozenset(range(1, n + 1))
+        return SSet([(self.cmp("<=", j + 1, n), j + 1) for j in range(len(items))], distinct=True)
+
+    def seq_eq(self, a, b):
+        na, ia = self.seq_parts(a)
+        nb, ib = self.seq_parts(b)
+        same_len = self.eq(na, nb)
+        if same_len is False:
+            return False
+        terms = [same_len]
+        for j in range(min(len(ia), len(ib))):
+            if is_int_const(na) and j >= na or is_int_const(nb) and j >= nb:
+                break
+            beyond = False if is_int_const(na) else self.cmp("<=", na, j)
+            terms.append(self.b_or([beyond, self.eq(ia[j], ib[j])]))
+        return self.b_and(terms)
+
+    def seq_mux(self, c, a, b):
+        na, ia = self.seq_parts(a)
+        nb, ib = self.seq_parts(b)
+        n = self.mux(c, na, nb)
+        items = []
+        for j in range(max(len(ia), len(ib))):
+            if j >= len(ia):
+                items.append(ib[j])
+            elif j >= len(ib):
+                items.append(ia[j])
+            else:
+                items.append(self.mux(c, ia[j], ib[j]))
+        return self.mk_seq(n, items)
+
+    def seq_except(self, v, idx, leaf):
+        """[v EXCEPT ![idx] = leaf(old item)]"""
+        n, items = self.seq_parts(v)
+        new = []
+        for j, old in enumerate(items):
+            c = self.eq(idx, j + 1)
+            new.append(old if c is False else self.mux(c, leaf(old), old))
+        return self.mk_seq(n, new)
+
+    SEQ_BUILTINS = {"Len": 1, "Head": 1, "Tail": 1, "Append": 2, "SubSeq": 3, "Seq": 1}
+
+    def seq_builtin(self, name, args):
+        if name == "Seq":
+            return SLazy("seq", args[0])
+        if name == "Len":
+            return self.seq_parts(args[0])[0]
+        if name == "Head":
+            return self.seq_at(args[0], 1)
+        if name == "Tail":
+            return self.seq_tail(args[0])
+        if name == "Append":
+            return self.seq_append(args[0], args[1])
+        return self.seq_subseq(args[0], args[1], args[2])
 
     # ------------------------------------------------------------ evaluation
     def force(self, t: Thunk):
@@ -777,6 +961,8 @@ class Lowerer:
                         raise LowerError("Permutations of a non-constant set")
                     elems = sorted(base, key=sort_key)
                     return frozenset(FnVal(dict(zip(elems, p))) for p in itertools.permutations(elems))
+                if k == "app" and self.SEQ_BUILTINS.get(e[1]) == len(e[2]):
+                    return self.seq_builtin(e[1], [self.ev(x, ctx, fm, env, S) for x in e[2]])
                 raise LowerError(f"unknown operator {e[1]}")
             target, defctx, args = op
             if not isinstance(target, Closure) and not target.params:
@@ -867,6 +1053,8 @@ class Lowerer:
             return SLazy("powerset", self.ev(e[1], ctx, fm, env, S))
         if k == "domain":
             f = self.ev(e[1], ctx, fm, env, S)
+            if not isinstance(f, SUnion) and kind_sig(f) == "tuple":
+                return self.seq_domain(f)
             return frozenset(self.fn_map(f))
         if k == "fnlit":
             keys, vals = [], []
@@ -883,6 +1071,8 @@ class Lowerer:
             args = [self.ev(a, ctx, fm, env, S) for a in e[2]]
             if len(args) != 1:
                 raise LowerError("multi-argument function application is not supported")
+            if not isinstance(f, SUnion) and kind_sig(f) == "tuple":
+                return self.seq_at(f, args[0])
             return self.fn_apply(f, args[0])
         if k == "fnset":
             return SLazy("fnset", self.ev(e[1], ctx, fm, env, S), self.ev(e[2], ctx, fm, env, S))
@@ -903,7 +1093,13 @@ class Lowerer:
         if k == "at":
             return env["@"]
         if k == "tuple":
-            return tuple(self.ev(x, ctx, fm, env, S) for x in e[1])
+            items = [self.ev(x, ctx, fm, env, S) for x in e[1]]
+            return self.mk_seq(len(items), items)
+        if k == "cross":
+            parts = [self.ev(x, ctx, fm, env, S) for x in e[1]]
+            if all(isinstance(p, frozenset) for p in parts):
+                return frozenset(tuple(c) for c in itertools.product(*[sorted(p, key=sort_key) for p in parts]))
+            return SLazy("cross", parts)
         if k == "prime":
             st1 = env.get("'")
             if st1 is None:
@@ -952,6 +1148,8 @@ class Lowerer:
             return self.mk_int(f"({A.s} * {B.s})", min(c), max(c))
         if op == "..":
             return self.interval(a, b)
+        if op == "\\o":
+            return self.seq_concat(a, b)
         if op == "\\in":
             return self.member(a, b)
         if op == "\\notin":
@@ -1033,6 +1231,8 @@ class Lowerer:
             fields[key] = self.except_leaf(fields[key], path, rhs, ctx, fm, env, S)
             return FnVal(fields) if all(is_const(v) for v in fields.values()) else SRec(fields)
         idx = self.ev(step[1], ctx, fm, env, S)
+        if not isinstance(f, SUnion) and kind_sig(f) == "tuple":
+            return self.seq_except(f, idx, lambda old: self.except_leaf(old, path, rhs, ctx, fm, env, S))
         m = self.fn_map(f)
         keys = list(f.keys) if isinstance(f, SFn) else [k for k, _ in f.items]
         if is_const(idx):

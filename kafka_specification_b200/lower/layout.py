@@ -19,6 +19,11 @@ TPrefixFn       function over 0..n-1 into X \\union {Nil} whose Nil entries are 
                 length field (checked; FiniteReplicatedLog.tla:84-87 states it): only X is coded
                 (``\\* kspec: PREFIX v arrayField lengthField``)
 
+TTuple          fixed-length tuple (an element of S \\X T): one member per position
+TSeq            sequence of at most ``cap`` scalar-codeable elements (``v \\in Seq(S)`` + ``\\* kspec: CAPACITY v = cap``):
+                a length field and cap element codes; the slots at index >= length hold code 0, so equal sequences
+                pack to equal bits
+
 Every type offers the same operations in two worlds: ``py_*`` on Python values (Init states,
 decoding traces, tests) and ``read``/``write``/``enc``/``dec`` on symbolic values, emitting C.
 """
@@ -26,7 +31,7 @@ from __future__ import annotations
 
 from ..frontend.cfg import ModelValue
 from ..frontend.values import FnVal, fmt, sort_key
-from .svals import (LowerError, SAtom, SBool, SFn, SInt, SRec, SSet, SUnion, is_atom_const,
+from .svals import (LowerError, SAtom, SBool, SFn, SInt, SRec, SSeq, SSet, SUnion, is_atom_const,
                     is_const, is_int_const, kind_sig)
 
 
@@ -1022,3 +1027,191 @@ class TPrefixFn(Ty):
             xv = lw.narrow_union(x, t.kind()) if isinstance(x, SUnion) else x
             c = lw.encode(t, xv)
             out[t.atom.index] = c if expect_nil is False else lw.tmp_int(f"({lw.bstr(expect_nil)} ? 0 : {c})")
+
+
+class TTuple(Ty):
+    """Fixed-length tuple <<x1, ..., xn>> (an element of a Cartesian product): one member type per position."""
+
+    def __init__(self, elems: list):
+        self.elems = list(elems)
+        self.card = 1
+        for t in self.elems:
+            self.card = self.card * t.card if (t.card and self.card) else 0
+        if self.card > (1 << 30):
+            self.card = 0
+        self.atom = None
+
+    def kind(self):
+        return "tuple"
+
+    def describe(self):
+        return {"t": "tuple", "elems": [t.describe() for t in self.elems]}
+
+    def alloc(self, lay, path):
+        for i, t in enumerate(self.elems):
+            t.alloc(lay, f"{path}[{i + 1}]")
+
+    def _items(self, v):
+        if isinstance(v, tuple):
+            items = list(v)
+        elif isinstance(v, SSeq) and is_int_const(v.n):
+            items = list(v.items[:v.n])
+        else:
+            raise LowerError(f"cannot store {v!r} in a tuple of {len(self.elems)}")
+        if len(items) != len(self.elems):
+            raise LowerError(f"tuple of length {len(items)} stored in a layout of length {len(self.elems)}")
+        return items
+
+    def py_enc(self, v):
+        code, stride = 0, 1
+        for t, x in zip(self.elems, self._items(v)):
+            code += t.py_enc(x) * stride
+            stride *= t.card
+        return code
+
+    def py_dec(self, code):
+        out = []
+        for t in self.elems:
+            out.append(t.py_dec(code % t.card))
+            code //= t.card
+        return tuple(out)
+
+    def py_write(self, v, codes):
+        for t, x in zip(self.elems, self._items(v)):
+            t.py_write(x, codes)
+
+    def py_read(self, codes):
+        return tuple(t.py_read(codes) for t in self.elems)
+
+    def enc(self, lw, v):
+        if is_const(v):
+            return str(self.py_enc(v))
+        if isinstance(v, SUnion):
+            return lw.enc_union_into(self, v)
+        terms, stride = [], 1
+        for t, x in zip(self.elems, self._items(v)):
+            c = lw.encode(t, x)
+            terms.append(c if stride == 1 else f"{c} * {stride}")
+            stride *= t.card
+        return lw.tmp_int("(" + " + ".join(terms) + ")")
+
+    def dec(self, lw, code):
+        out, stride = [], 1
+        for t in self.elems:
+            if t.card == 1:
+                out.append(t.py_dec(0))
+            else:
+                x = code if stride == 1 else f"({code} / {stride})"
+                if stride * t.card < self.card:
+                    x = f"({x} % {t.card})"
+                out.append(t.dec(lw, lw.tmp_int(x)))
+            stride *= t.card
+        return lw.mk_seq(len(out), out)
+
+    def read(self, lw):
+        items = [lw.read_ty(t) for t in self.elems]
+        return lw.mk_seq(len(items), items)
+
+    def write(self, lw, v, out):
+        if isinstance(v, SUnion):
+            v = lw.narrow_union(v, "tuple")
+        for t, x in zip(self.elems, self._items(v)):
+            if x is lw.read_cache.get(id(t)):
+                continue
+            t.write(lw, x, out)
+
+
+class TSeq(Ty):
+    """Sequence of at most ``cap`` elements of a scalar-codeable type: length atom + one code atom per slot;
+    unused slots hold code 0 (canonical packing).  A longer sequence traps (KMC_E_LAYOUT_OVERFLOW)."""
+
+    def __init__(self, elem: Ty, cap: int | None = None):
+        if not elem.card:
+            raise LowerError("Seq(S): the element type must be codeable as one integer (scalars, small records)")
+        self.elem, self.cap = elem, cap
+        self.card = 0
+        self.atom = None
+        self.len_ty = None
+        self.slots: list[Ty] = []
+
+    def set_cap(self, cap: int):
+        self.cap = cap
+        self._sig = None
+
+    def kind(self):
+        return "tuple"
+
+    def describe(self):
+        return {"t": "seq", "cap": self.cap, "elem": self.elem.describe()}
+
+    def alloc(self, lay, path):
+        import copy
+        if self.cap is None:
+            raise LowerError(f"{path} \\in Seq(...) needs a bound: add '\\* kspec: CAPACITY {path} = <max length>' to the cfg")
+        self.len_ty = TInt(0, self.cap)
+        self.len_ty.alloc(lay, f"{path}.len")
+        # every slot is ONE atom holding the element's scalar code (mixed radix for records), like the slots of an
+        # array set -- not the per-field atoms a top-level record would get
+        self.slots = [copy.deepcopy(self.elem) for _ in range(self.cap)]
+        for i, t in enumerate(self.slots):
+            t._alloc_scalar(lay, f"{path}[{i + 1}]")
+
+    def py_write(self, v, codes):
+        if not isinstance(v, tuple) or len(v) > self.cap:
+            raise LowerError(f"value {fmt(v)} is not a sequence of at most {self.cap} elements")
+        if self.len_ty.atom is not None:
+            codes[self.len_ty.atom.index] = len(v)
+        for i, t in enumerate(self.slots):
+            code = t.py_enc(v[i]) if i < len(v) else 0
+            if t.atom is not None:
+                codes[t.atom.index] = code
+
+    def py_read(self, codes):
+        n = codes[self.len_ty.atom.index] if self.len_ty.atom is not None else 0
+        return tuple(t.py_dec(codes[t.atom.index] if t.atom is not None else 0) for t in self.slots[:n])
+
+    def read(self, lw):
+        n = lw.read_ty(self.len_ty)
+        items = []
+        for t in self.slots:
+            v = Ty.read(t, lw)                     # scalar read: dec(a<idx>), remembered as that code
+            lw.read_cache[id(t)] = v
+            items.append(v)
+        return lw.mk_seq(n, items)
+
+    def write(self, lw, v, out):
+        if isinstance(v, SUnion):
+            v = lw.narrow_union(v, "tuple")
+        n, items = lw.seq_parts(v)
+        if is_int_const(n):
+            if n > self.cap:
+                lw.trap_unless(False)
+                return
+        elif n.hi > self.cap:
+            lw.trap_unless(lw.cmp("<=", n, self.cap))
+        if self.len_ty.atom is not None:
+            out[self.len_ty.atom.index] = str(n) if is_int_const(n) else n.s
+        for j, t in enumerate(self.slots):
+            if t.atom is None:
+                continue
+            if j >= len(items) or (is_int_const(n) and j >= n):
+                out[t.atom.index] = "0"
+                continue
+            if is_int_const(n):
+                out[t.atom.index] = lw.encode(t, items[j])
+                continue
+            # slot j is live iff j < n; a dead slot packs to 0.  Range traps of a dead item must not fire: its
+            # traps are folded into the live condition.
+            marks = len(lw.traps)
+            code = lw.encode(t, items[j])
+            live = lw.cmp(">", n, j)
+            new_traps = lw.traps[marks:]
+            del lw.traps[marks:]
+            for tr in new_traps:
+                lw.trap_unless(lw.b_or([lw.b_not(live), tr]))
+            if live is True:
+                out[t.atom.index] = code
+            elif live is False:
+                out[t.atom.index] = "0"
+            else:
+                out[t.atom.index] = lw.tmp_int(f"({live.s} ? {code} : 0)")

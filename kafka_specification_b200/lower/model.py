@@ -82,6 +82,10 @@ class TypeInference:
                 return L.TSet(self.type_from_setval(v.a))
             if v.kind == "union":
                 return self.merge(self.type_from_setval(v.a), self.type_from_setval(v.b))
+            if v.kind == "seq":
+                return L.TSeq(self.type_from_setval(v.a))          # the bound comes from the cfg's CAPACITY hint
+            if v.kind == "cross":
+                return L.TTuple([self.type_from_setval(p) for p in v.a])
             raise LowerError(f"unbounded set {v.kind} in a layout type: give the variable a bounded "
                              f"type through a '\\* kspec: LAYOUT Op' operator")
         if not isinstance(v, frozenset):
@@ -93,7 +97,12 @@ class TypeInference:
         atoms = [x for x in v if is_atom_const(x)]
         recs = [x for x in v if isinstance(x, FnVal)]
         sets = [x for x in v if isinstance(x, frozenset)]
+        tups = [x for x in v if isinstance(x, tuple)]
         parts: list[L.Ty] = []
+        if tups:
+            if len({len(t) for t in tups}) != 1:
+                raise LowerError("layout type mixes tuples of different lengths (use Seq(S) with a CAPACITY hint)")
+            parts.append(L.TTuple([self.type_from_setval(frozenset(t[i] for t in tups)) for i in range(len(tups[0]))]))
         if bools:
             parts.append(L.TBool())
         if ints:
@@ -114,7 +123,7 @@ class TypeInference:
         if sets:
             universe = frozenset().union(*sets)
             parts.append(L.TSet(self.type_from_setval(universe), nonempty=frozenset() not in sets))
-        if len(bools) + len(ints) + len(atoms) + len(recs) + len(sets) != len(v):
+        if len(bools) + len(ints) + len(atoms) + len(recs) + len(sets) + len(tups) != len(v):
             raise LowerError("unsupported element kind in a layout type")
         return parts[0] if len(parts) == 1 else L.TUnion(sorted(parts, key=lambda t: t.kind()))
 
@@ -548,12 +557,15 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
                 raise LowerError(f"KEYED given for {v}, which is not a set")
             ty = L.TKeyedSet(ty.elem, cfg.keyed[v])
         elif v in cfg.capacities:
-            if not isinstance(ty, L.TSet):
-                raise LowerError(f"CAPACITY given for {v}, which is not a set")
+            if not isinstance(ty, (L.TSet, L.TSeq)):
+                raise LowerError(f"CAPACITY given for {v}, which is neither a set nor a sequence")
             cap = lw.ev(parse_expression_text(cfg.capacities[v]), root, None, {}, None)
             if not is_int_const(cap) or cap < 0:
                 raise LowerError(f"CAPACITY {v} does not evaluate to a natural number")
-            ty = L.TSet(ty.elem, cap)
+            if isinstance(ty, L.TSeq):
+                ty.set_cap(cap)
+            else:
+                ty = L.TSet(ty.elem, cap)
         if v in cfg.prefix:
             apply_prefix(ty, *cfg.prefix[v])
         lay.var_types[v] = ty

@@ -11,7 +11,9 @@ are C expression strings over the unpacked state atoms.
   SRec   record with symbolic fields          SFn   function over a constant finite domain
   SSet   guarded element list [(guard, elem)] -- the set of elems whose guard holds
   SUnion value of one of several kinds [(guard, value)], guards mutually exclusive
-  SLazy  non-enumerated constant set descriptor (record sets, function sets, SUBSET, Nat)
+  SLazy  non-enumerated constant set descriptor (record sets, function sets, SUBSET, Nat, Seq(S), S \\X T)
+  SSeq   sequence / tuple: a length (int or SInt) and ``cap`` item values; item i (0-based) is meaningful
+         iff i < length.  A fully constant sequence is a Python tuple.
 """
 from __future__ import annotations
 
@@ -94,18 +96,32 @@ class SUnion:
         return f"SUnion({self.alts})"
 
 
+class SSeq:
+    __slots__ = ("n", "items")
+
+    def __init__(self, n, items: list):
+        self.n, self.items = n, list(items)     # n: int or SInt with hi <= len(items)
+
+    @property
+    def cap(self) -> int:
+        return len(self.items)
+
+    def __repr__(self):
+        return f"SSeq(len={self.n}, {self.items})"
+
+
 class SLazy:
     """Constant set descriptors that are never enumerated unless asked to."""
     __slots__ = ("kind", "a", "b")
 
     def __init__(self, kind: str, a=None, b=None):
-        self.kind, self.a, self.b = kind, a, b   # 'nat' | 'int' | 'recset'(a=dict) | 'fnset'(a=dom,b=rng) | 'powerset'(a=base) | 'union'(a,b)
+        self.kind, self.a, self.b = kind, a, b   # 'nat' | 'int' | 'recset'(a=dict) | 'fnset'(a=dom,b=rng) | 'powerset'(a=base) | 'union'(a,b) | 'seq'(a=elem set) | 'cross'(a=[sets])
 
     def __repr__(self):
         return f"SLazy({self.kind}, {self.a}, {self.b})"
 
 
-SYMBOLIC = (SInt, SBool, SAtom, SRec, SFn, SSet, SUnion, SLazy)
+SYMBOLIC = (SInt, SBool, SAtom, SRec, SFn, SSet, SUnion, SLazy, SSeq)
 
 
 def is_const(v) -> bool:
@@ -129,6 +145,8 @@ def is_static(v) -> bool:
             return True
         if v.kind == "recset":
             return all(is_static(x) for x in v.a.values())
+        if v.kind == "cross":
+            return all(is_static(x) for x in v.a)
         return is_static(v.a) and (v.b is None or is_static(v.b))
     return False
 
@@ -154,6 +172,6 @@ def kind_sig(v) -> str:
         return "set"
     if isinstance(v, SUnion):
         return "union"
-    if isinstance(v, tuple):
+    if isinstance(v, (tuple, SSeq)):
         return "tuple"
     raise LowerError(f"unknown value kind {v!r}")

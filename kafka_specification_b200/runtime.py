@@ -171,6 +171,11 @@ class StateDecoder:
             return c
         if k == "fn":
             return self._card(t["elem"]) ** len(t["keys"])
+        if k == "tuple":
+            c = 1
+            for e in t["elems"]:
+                c *= self._card(e)
+            return c
         if k == "union":
             return sum(self._card(a) for a in t["alts"])
         if k == "set":
@@ -199,6 +204,13 @@ class StateDecoder:
                 d[_parse_atom(key)] = self._dec(t["elem"], code % c)
                 code //= c
             return FnVal(d)
+        if k == "tuple":
+            out = []
+            for e in t["elems"]:
+                c = self._card(e)
+                out.append(self._dec(e, code % c))
+                code //= c
+            return tuple(out)
         if k == "union":
             off = 0
             for a in t["alts"]:
@@ -236,6 +248,21 @@ class StateDecoder:
             return FnVal(d)
         if k == "fn":
             return FnVal({_parse_atom(key): self._read(t["elem"], codes, pos) for key in t["keys"]})
+        if k == "tuple":
+            return tuple(self._read(e, codes, pos) for e in t["elems"])
+        if k == "seq":
+            n = 0
+            if t["cap"] > 0:
+                n = codes[pos[0]]
+                pos[0] += 1
+            items = []
+            for _ in range(t["cap"]):              # one scalar code per slot (mixed radix for record elements)
+                if _bits_for(self._card(t["elem"])) == 0:
+                    items.append(self._dec(t["elem"], 0))
+                else:
+                    items.append(self._dec(t["elem"], codes[pos[0]]))
+                    pos[0] += 1
+            return tuple(items[:n])
         if k == "set":
             if t["repr"] == "keyed":
                 key, fields = t["key"], t["elem"]["fields"]

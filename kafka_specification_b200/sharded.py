@@ -29,7 +29,7 @@ from dataclasses import dataclass, field
 import torch
 import torch.distributed as dist
 
-from .runtime import Checker, ShardBuffers
+from .runtime import Checker, KmcError, ShardBuffers
 
 
 class ShardEngine:
@@ -300,6 +300,18 @@ class ShardedChecker:
         if hasattr(e, "count_matrix"):
             matrix = e.count_matrix(self.group)
             counts = matrix[self.rank]
+            # Every rank holds the same matrix, so every rank takes the same decision here: an overflowed owner
+            # region (the expand kernel's counters keep counting past region_rows) or an inbox that cannot take
+            # what is coming ends the run on ALL ranks before any row is exchanged -- never on one rank only,
+            # with the others blocked inside the all-to-all.
+            cap, rcap = getattr(e, "region_rows", None), getattr(e, "recv_rows_cap", None)
+            if cap is not None and any(x > cap for row in matrix for x in row):
+                raise KmcError(-10, "candidate buffer overflow (raise cand_bytes or fanout_bound): an owner region of "
+                                    f"{cap} rows was asked to hold {max(x for row in matrix for x in row)}")
+            if rcap is not None:
+                worst = max(sum(matrix[src][dst] for src in range(self.world)) for dst in range(self.world))
+                if worst > rcap:
+                    raise KmcError(-10, f"{worst} incoming rows exceed a rank's receive buffer ({rcap} rows); raise cand_bytes")
         else:
             matrix, counts = None, e.counts()
         rows = self._exchange(counts, matrix)

@@ -129,6 +129,39 @@ class PowerSet(LazySet):
         return f"SUBSET {self.base!r}"
 
 
+class SeqSet(LazySet):
+    """Seq(S): every finite sequence over S -- membership only, never enumerated."""
+
+    def __init__(self, base):
+        self.base = base
+
+    def __contains__(self, v):
+        return isinstance(v, tuple) and all(set_contains(self.base, x) for x in v)
+
+    def enumerate(self):
+        raise EvalError("Seq(S) is infinite and cannot be enumerated")
+
+    def __repr__(self):
+        return f"Seq({self.base!r})"
+
+
+class CrossSet(LazySet):
+    """S1 \\X ... \\X Sn with a component that is not enumerable (e.g. Nat): membership only."""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+    def __contains__(self, v):
+        return isinstance(v, tuple) and len(v) == len(self.parts) and all(set_contains(s, x) for s, x in zip(self.parts, v))
+
+    def enumerate(self):
+        for combo in itertools.product(*[sorted(set_elems(s), key=sort_key) for s in self.parts]):
+            yield tuple(combo)
+
+    def __repr__(self):
+        return " \\X ".join(repr(s) for s in self.parts)
+
+
 class UnionSet(LazySet):
     def __init__(self, a, b):
         self.a, self.b = a, b
@@ -186,6 +219,36 @@ def kind_of(v) -> str:
     if isinstance(v, tuple):
         return "tuple"
     raise EvalError(f"unknown value kind {v!r}")
+
+
+# module Sequences (a sequence is a Python tuple)
+SEQ_BUILTINS = {"Len": 1, "Head": 1, "Tail": 1, "Append": 2, "SubSeq": 3, "Seq": 1}
+
+
+def seq_builtin(name, args):
+    if name == "Seq":
+        return SeqSet(args[0])
+    s = args[0]
+    if not isinstance(s, tuple):
+        raise EvalError(f"{name} applied to the non-sequence {fmt(s)}")
+    if name == "Len":
+        return len(s)
+    if name == "Head":
+        if not s:
+            raise EvalError("Head of the empty sequence")
+        return s[0]
+    if name == "Tail":
+        if not s:
+            raise EvalError("Tail of the empty sequence")
+        return s[1:]
+    if name == "Append":
+        return s + (args[1],)
+    m, k = args[1], args[2]
+    if k < m:
+        return ()
+    if m < 1 or k > len(s):
+        raise EvalError(f"SubSeq bounds {m}..{k} outside 1..{len(s)}")
+    return s[m - 1:k]
 
 
 def tla_eq(a, b) -> bool:
@@ -354,6 +417,8 @@ class Interp:
                     # TLC module: the set of all permutations (bijections S -> S) of a finite set
                     elems = sorted(set_elems(self.ev(e[2][0], ctx, fm, env, st, st1)), key=sort_key)
                     return frozenset(FnVal(dict(zip(elems, p))) for p in itertools.permutations(elems))
+                if k == "app" and SEQ_BUILTINS.get(e[1]) == len(e[2]):
+                    return seq_builtin(e[1], [self.ev(x, ctx, fm, env, st, st1) for x in e[2]])
                 raise EvalError(f"unknown operator {e[1]}")
             target, defctx, args = op
             if k == "inst" and not target.params:
@@ -440,6 +505,8 @@ class Interp:
             return frozenset(out)
         if k == "domain":
             f = self.ev(e[1], ctx, fm, env, st, st1)
+            if isinstance(f, tuple):
+                return frozenset(range(1, len(f) + 1))
             if not isinstance(f, FnVal):
                 raise EvalError("DOMAIN of a non-function")
             return f.domain()
@@ -452,6 +519,10 @@ class Interp:
             f = self.ev(e[1], ctx, fm, env, st, st1)
             args = [self.ev(a, ctx, fm, env, st, st1) for a in e[2]]
             key = args[0] if len(args) == 1 else tuple(args)
+            if isinstance(f, tuple):
+                if isinstance(key, bool) or not isinstance(key, int) or not 1 <= key <= len(f):
+                    raise EvalError(f"sequence index {fmt(key)} outside 1..{len(f)}")
+                return f[key - 1]
             if not isinstance(f, FnVal):
                 raise EvalError(f"applying non-function {fmt(f)}")
             return f.apply(key)
@@ -486,6 +557,10 @@ class Interp:
             return env["@"]
         if k == "tuple":
             return tuple(self.ev(x, ctx, fm, env, st, st1) for x in e[1])
+        if k == "cross":
+            parts = [self.ev(x, ctx, fm, env, st, st1) for x in e[1]]
+            cs = CrossSet(parts)
+            return cs.materialize() if all(isinstance(p, frozenset) for p in parts) else cs
         if k == "prime":
             if st1 is None:
                 raise EvalError("primed expression outside an action")
@@ -542,6 +617,10 @@ class Interp:
             if op == "\\div":
                 return a // b
             return frozenset(range(a, b + 1))
+        if op == "\\o":
+            if not isinstance(a, tuple) or not isinstance(b, tuple):
+                raise EvalError("\\o applied to a non-sequence")
+            return a + b
         if op == "\\in":
             return set_contains(b, a)
         if op == "\\notin":
@@ -591,9 +670,20 @@ class Interp:
 
     def except_update(self, f, path, rhs, ctx, fm, env, st, st1):
         step = path[0]
+        key = self.ev(step[1], ctx, fm, env, st, st1) if step[0] == "idx" else step[1]
+        if isinstance(f, tuple):
+            if isinstance(key, bool) or not isinstance(key, int) or not 1 <= key <= len(f):
+                raise EvalError(f"EXCEPT on sequence index {fmt(key)} outside 1..{len(f)}")
+            old = f[key - 1]
+            if len(path) == 1:
+                env2 = dict(env)
+                env2["@"] = old
+                new = self.ev(rhs, ctx, fm, env2, st, st1)
+            else:
+                new = self.except_update(old, path[1:], rhs, ctx, fm, env, st, st1)
+            return f[:key - 1] + (new,) + f[key:]
         if not isinstance(f, FnVal):
             raise EvalError("EXCEPT applied to a non-function")
-        key = self.ev(step[1], ctx, fm, env, st, st1) if step[0] == "idx" else step[1]
         old = f.apply(key)
         if len(path) == 1:
             env2 = dict(env)
