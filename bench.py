@@ -168,8 +168,10 @@ def cpu_scaling(model: str):
 
 def config_for(model: str, extra: dict | None = None) -> dict:
     reg = load_json(os.path.join(ROOT, "models", "MODELS.json"))[model]
-    c = {"workload": f"{reg['module']} ({reg['cfg']}): full BFS, KafkaReplication.tla 3 brokers LogSize 4, "
-                     f"kso params {(reg.get('kso') or [None, None])[1]}",
+    params = (reg.get("kso") or [None, None])[1]
+    what = (f"KafkaReplication.tla {params[0]} brokers LogSize {params[1]} MaxRecords {params[2]} MaxLeaderEpoch {params[3]}"
+            if params and len(params) == 4 else f"params {params}")
+    c = {"workload": f"{reg['module']} ({reg['cfg']}): full BFS, {what}",
          "model": model, "l2": "inputs larger than L2: hash set and state store are GBs and the set is reset every step"}
     if extra:
         c.update(extra)
@@ -182,10 +184,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # a CPU run has no clocks to ramp and no caches worth warming across 10^8-state searches: one warm-up run at most,
+    # and a per-step budget that keeps the whole arm (probe + steps + the two scaling samples) to a few minutes
+    warm = min(args.warmup, 1)
+    budget = max(10.0, min(40.0, 150.0 / (warm + args.steps)))
     vals = []
-    for i in range(args.warmup + args.steps):
-        s = cpu_run(args.model, budget_s=40.0)
-        if i >= args.warmup:
+    for i in range(warm + args.steps):
+        s = cpu_run(args.model, budget_s=budget)
+        if i >= warm:
             vals.append(s)
     total_states = sum(v["distinct"] for v in vals)
     total_s = sum(v["seconds"] for v in vals)
