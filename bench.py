@@ -101,6 +101,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def nvlink_counters(gpu_index: int):
+    """Cumulative NVLink data counters of one GPU (sum over its links), in bytes, from `nvidia-smi nvlink -gt d`
+    ("Data Tx: N KiB" / "Data Rx: N KiB" per link); None when the tool, the option or the links are not there."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx or not rx:
+        return None
+    return {"tx": 1024 * sum(tx), "rx": 1024 * sum(rx), "links": len(tx)}
+
+
 def golden_for(model: str):
     g = load_json(os.path.join(ROOT, "tests", "golden", "goldens.json"))
     return g.get(model)
@@ -412,6 +428,7 @@ def run_sharded(args):
         sampler.start()
     dist.barrier()
     torch.cuda.synchronize()
+    nvl0 = nvlink_counters(local) if rank == 0 else None
     secs, gpu_ms, launches = [], [], 0
     ins_ms = exp_ms = 0.0
     n_ins = n_exp = 0
@@ -435,6 +452,13 @@ def run_sharded(args):
     lt = torch.tensor([launches], dtype=torch.int64, device=eng.device)
     dist.all_reduce(lt)
     clocks = sampler.stop() if rank == 0 else None
+    nvl1 = nvlink_counters(local) if rank == 0 else None
+    nvlink_measured = None
+    if nvl0 and nvl1:
+        nvlink_measured = {"gpu": local, "links": nvl1["links"],
+                           "tx_bytes_per_step": (nvl1["tx"] - nvl0["tx"]) / max(1, args.steps),
+                           "rx_bytes_per_step": (nvl1["rx"] - nvl0["rx"]) / max(1, args.steps),
+                           "source": "nvidia-smi nvlink -gt d, rank 0's GPU, counters read before and after the timed steps"}
     if rank == 0:
         parity = check_result(args.model, res.distinct, res.generated, res.depth, res.levels, res.deadlocks)
         steps = args.steps
@@ -458,6 +482,7 @@ def run_sharded(args):
                                                              "stream-ordered NCCL barrier per round, host read-back per level"),
                                               "round_sync_note": sync_note,
                                               "nvlink_bytes_per_step_est": int(G * (world - 1) / world * (W + 1) * 8),
+                                              "nvlink_measured": nvlink_measured,
                                               "per_rank_distinct": res.per_rank_distinct,
                                               "exchanged_rows_per_step": res.exchanged_rows}),
             "roofline": {"kernel": "k_insert (rank 0)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
