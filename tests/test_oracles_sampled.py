@@ -99,3 +99,56 @@ def test_random_walks_agree_with_oracle_a_step_by_step(name, walks, steps, regis
             cur = nxt[rng.randrange(len(nxt))].copy()
     assert compared >= walks * 5 and deepest >= min(steps, 12)
     print(f"[walks] {name}: {walks} walks, {compared} states compared step by step, deepest step {deepest}")
+
+
+@needs_reference
+@pytest.mark.parametrize("name,walks,steps", [("kip320sym_3x4_r4e3", 4, 40), ("kip320sym_5brokers", 2, 35)])
+def test_canonicalize_is_an_orbit_invariant_on_deep_states(name, walks, steps, registry):
+    """SYMMETRY at headline size (3! permutations) and for config #4 (5! = 120): on the states of random walks the lowered
+    canonicalize() (what the GPU fingerprints) must be (a) the same for every permuted image of the state -- images
+    built with Oracle A's permute_value on the decoded TLA values, packed by the layout --, (b) one of those images,
+    (c) idempotent.  Together: it picks one representative per orbit, which is all TLC's symmetry reduction needs."""
+    import itertools
+    import tla_interp
+    spec = registry[name]
+    cfg_text = open(os.path.join(ROOT, spec["cfg"])).read()
+    m = lower_model(spec["module"], DIRS, cfg_text, name=name)
+    lib = build_host(m)
+    W = m.words
+    lib.kmc_host_successors.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.kmc_host_canonicalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.kmc_host_init_state.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.kmc_host_in_model.argtypes = [ctypes.c_void_p]
+    lay = m.lowerer.layout
+    replicas = sorted(m.decode_state(np.array(m.init_states[0], dtype=np.uint64))["replicaLog"].domain(), key=str)
+    perms = [dict(zip(replicas, p)) for p in itertools.permutations(replicas)]
+
+    def canon(words):
+        w = np.array(words, dtype=np.uint64)
+        out = np.zeros(W, dtype=np.uint64)
+        lib.kmc_host_canonicalize(w.ctypes.data, out.ctypes.data)
+        return tuple(int(x) for x in out)
+
+    rng = random.Random(7 + len(name))
+    cap = max(512, 4 * m.max_fanout)
+    out = np.zeros((cap, W), dtype=np.uint64)
+    checked = 0
+    for _ in range(walks):
+        cur = np.array(m.init_states[0], dtype=np.uint64)
+        for step in range(steps):
+            st = m.decode_state(cur)
+            c0 = canon(cur)
+            images = set()
+            for pm in perms:
+                img = {v: tla_interp.permute_value(st[v], pm) for v in m.variables}
+                words = lay.py_pack(img)
+                images.add(tuple(words))
+                assert canon(words) == c0, (name, step, pm)
+            assert c0 in images and canon(c0) == c0
+            checked += 1
+            n = lib.kmc_host_successors(cur.ctypes.data, 0, out.ctypes.data, None, cap)
+            assert 0 < n <= cap or n == 0
+            if n == 0:
+                break
+            cur = out[rng.randrange(n)].copy()
+    assert checked >= walks * 10
