@@ -67,6 +67,11 @@ def test_random_walks_agree_with_oracle_a_step_by_step(name, walks, steps, regis
     assert sorted(m.state_text(w) for w in l_inits) == a_inits
 
     walks *= int(os.environ.get("KSPEC_WALK_SCALE", "1"))          # (a longer offline run: KSPEC_WALK_SCALE=10)
+    kafka_b = None
+    if spec.get("kso") and "replicaLog" in variables:
+        import kso
+        kafka_b = tuple(spec["kso"])
+        replicas = sorted(m.decode_state(l_inits[0])["replicaLog"].domain(), key=str)
     rng = random.Random(20260923 + len(name))
     cap = max(512, 4 * m.max_fanout)
     out = np.zeros((cap, W), dtype=np.uint64)
@@ -82,7 +87,17 @@ def test_random_walks_agree_with_oracle_a_step_by_step(name, walks, steps, regis
             inmodel_a = all(it.eval_named_predicate(c, st) for c in cfg.constraints)
             assert bool(lib.kmc_host_in_model(cur.ctypes.data)) == inmodel_a
             # successors: multiset of canonical texts, both forms of the lowered Next
-            want = sorted(_text(variables, s1) for s1 in it.next_states(next_e, st))
+            succ_a = it.next_states(next_e, st)
+            want = sorted(_text(variables, s1) for s1 in succ_a)
+            if kafka_b is not None:
+                # three-way: Oracle B (the hand-written C restatement all the large goldens come from) enumerates the
+                # same multiset of successors for this state and gives the same invariant verdicts as Oracle A
+                model_b, params_b = kafka_b
+                rec = kso.kstate_from_tla(st, replicas)
+                assert sorted(kso.successors(model_b, params_b, rec)) == sorted(kso.kstate_from_tla(s1, replicas) for s1 in succ_a), \
+                    (name, f"step {step}: Oracle B and Oracle A enumerate different successors for\n{m.state_text(cur)}")
+                inv_b = [i for i in cfg.invariants if i in kso.INVARIANTS]
+                assert set(kso.violated(model_b, params_b, rec, inv_b)) == {i for i in inv_b if not it.eval_named_predicate(i, st)}
             rows = None
             for items in (0, 1):
                 n = lib.kmc_host_successors(cur.ctypes.data, items, out.ctypes.data, None, cap)
