@@ -59,3 +59,25 @@ def test_sharded_bfs_stops_on_violation(tmp_path, goldens):
     assert len(r["trace_ranks"]) == 2                       # it does hop between the two ranks' stores
     r = _run("trunchw_n2", 2, 200, tmp_path, extra=("cont",))
     assert (r["distinct"], r["generated"], r["depth"]) == (g["distinct"], g["generated"], g["depth"])
+
+
+@pytest.mark.parametrize("name,world,chunk", [("kip320_n2", 2, 97), ("frl_tiny", 3, 7), ("asyncisr_v2", 2, 50)])
+def test_device_sync_driver_loop_matches_golden(name, world, chunk, tmp_path, goldens):
+    """The driver's side of the device-synchronised protocol (one board per level, rounds without collectives of its
+    own), over a stand-in whose rounds exchange through gloo: same counts and widths for any world size."""
+    g = goldens[name]
+    r = _run(name, world, chunk, tmp_path, extra=("board",))
+    assert (r["distinct"], r["generated"], r["depth"], r["deadlocks"]) == (
+        g["distinct"], g["generated"], g["depth"], g["deadlocks"])
+    assert r["levels"] == g["levels"] and r["complete"] and r["violation"] is None
+    assert sum(r["per_rank"]) == g["distinct"] and all(n > 0 for n in r["per_rank"])
+
+
+def test_device_sync_driver_loop_stops_on_violation(tmp_path, goldens):
+    g = goldens["trunchw_n2"]
+    first = min(l for l in g["first_violation_level"].values() if l)
+    r = _run("trunchw_n2", 2, 200, tmp_path, extra=("board",))
+    assert r["violation"] is not None and not r["complete"] and r["depth"] == first - 1
+    assert r["violation"]["level"] == first and r["trace_len"] == first and r["trace_ok"] is True
+    r = _run("trunchw_n2", 2, 200, tmp_path, extra=("board", "cont"))
+    assert (r["distinct"], r["generated"], r["depth"], r["levels"]) == (g["distinct"], g["generated"], g["depth"], g["levels"])
