@@ -12,13 +12,25 @@ package tlc2.gpu;
 public final class GpuModelChecker {
     public static void main(String[] args) {
         String config = null, spec = null, modelLib = System.getProperty("kspec.model");
-        boolean noDeadlock = false, cont = false;
+        boolean noDeadlock = false, cont = false, spill = false;
+        int gpus = 1, fpbits = 0;
+        String metadir = null, recover = null;
+        double checkpointMinutes = -1;
         for (int i = 0; i < args.length; i++) {
             switch (args[i]) {
                 case "-config": config = args[++i]; break;
                 case "-deadlock": noDeadlock = true; break;
                 case "-continue": cont = true; break;
-                case "-workers": i++; break;           // accepted, unused: the GPU grid replaces workers
+                case "-workers": {                     // N GPUs of this machine behind one context (option "gpus")
+                    String w = args[++i];
+                    gpus = w.equals("auto") ? 1 : Math.max(1, Integer.parseInt(w));
+                    break;
+                }
+                case "-fpbits": fpbits = Integer.parseInt(args[++i]); break;
+                case "-metadir": metadir = args[++i]; break;
+                case "-checkpoint": checkpointMinutes = Double.parseDouble(args[++i]); break;
+                case "-recover": recover = args[++i]; break;
+                case "-spill": spill = true; break;    // extension: old BFS levels move to host memory
                 default: spec = args[i];
             }
         }
@@ -29,6 +41,14 @@ public final class GpuModelChecker {
         StringBuilder opts = new StringBuilder("{");
         opts.append("\"continue\": ").append(cont);
         if (noDeadlock) opts.append(", \"check_deadlock\": false");
+        if (gpus > 1) opts.append(", \"gpus\": ").append(gpus);
+        if (fpbits > 0) opts.append(", \"table_log2\": ").append(fpbits);
+        if (spill) opts.append(", \"spill\": true");
+        if (metadir != null) {
+            opts.append(", \"checkpoint_dir\": \"").append(metadir).append("\"");
+            opts.append(", \"checkpoint_minutes\": ").append(checkpointMinutes < 0 ? 30.0 : checkpointMinutes);
+        }
+        if (recover != null) opts.append(", \"recover\": \"").append(recover).append("\"");
         opts.append("}");
         long ctx = Native.create(modelLib, opts.toString());
         int rc = Native.run(ctx);
