@@ -176,7 +176,7 @@ struct DevCounters {
 // parent/action word, the fingerprint and the invariant index (~0 = deadlock).  The host picks
 // the entry with the smallest fingerprint -> the reported counterexample is deterministic
 // (as long as the first violating level has <= VIOL_RING violators).
-static constexpr int VIOL_RING = 1024;
+static constexpr int VIOL_RING = 1 << 16;     // rows; (W + 3) * 8 bytes each: 2.6 MB for a two-word model
 static constexpr int VIOL_ROW = W + 3;
 
 struct Params {
