@@ -58,3 +58,19 @@ def test_zz_three_replica_state_sets_match_oracle_a(name, goldens):
         texts = ck.decoder.texts(ck.copy_states(0, r.distinct))
     assert r.distinct == g["distinct"] and len(set(texts)) == g["distinct"]
     assert state_digest(texts) == g["state_digest"]
+
+
+def test_zz_cli_runs_a_sequences_spec_end_to_end():
+    """.tla with module Sequences + .cfg in, TLC's summary out (lowering + nvcc + GPU run inside the CLI)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    specs = os.path.join(ROOT, "tests", "specs")
+    p = subprocess.run([sys.executable, "-m", "kafka_specification_b200.tlc2", "-config", os.path.join(specs, "MiniQueue.cfg"),
+                        "-deadlock", os.path.join(specs, "MiniQueue")], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out
+    assert "Model checking completed. No error has been found." in out
+    assert "729 states generated, 160 distinct states found, 0 states left on queue." in out
+    assert "The depth of the complete state graph search is 6." in out
