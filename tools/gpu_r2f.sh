@@ -28,7 +28,7 @@ timeout 900 python tools/bench_variants.py $M 3 '{"tag":"base"}' '{"tag":"overla
     > gpurun_out/r2f_variants.jsonl 2> gpurun_out/r2f_variants.err
 # 3. the four protocol variants at headline bounds and config #5 (throughput next to the headline)
 for m in trunchw_3x4_r3e3 kip101_3x4_r3e3 kip279_3x4_r3e3 firsttry_3x4_r3e3 asyncisr_deep; do
-  timeout 300 python tools/bench_variants.py $m 2 '{"tag":"base","continue":true}' >> gpurun_out/r2f_variants.jsonl 2>> gpurun_out/r2f_variants.err
+  timeout 300 python tools/bench_variants.py $m 2 '{"tag":"base"}' >> gpurun_out/r2f_variants.jsonl 2>> gpurun_out/r2f_variants.err
 done
 cat gpurun_out/r2f_variants.jsonl
 # 4. launch list + one full capture of each dominant kernel (same launches as r2c: second chunk of level 22)
