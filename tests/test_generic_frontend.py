@@ -139,3 +139,23 @@ def test_minimsgs_sequence_of_records():
     from kafka_specification_b200.runtime import StateDecoder
     dec = StateDecoder(m.meta())
     assert [dec.text(row) for row in r["states"]] == [m.state_text(row) for row in r["states"]]
+
+
+def test_miniwindow_runtime_bounds_and_products():
+    """tests/specs/MiniWindow.tla: SubSeq with a run-time lower bound, Len of a concatenation, \\E over 1 .. Len(s) with
+    a run-time index, a record with a tuple-valued field, membership in Nat \\X Nat."""
+    import numpy as np
+    import tla_interp
+    from kafka_specification_b200.runtime import StateDecoder
+    cfg = open(os.path.join(SPECS, "MiniWindow.cfg")).read()
+    a = tla_interp.run_bfs("MiniWindow", [SPECS], cfg, collect_states=True, stop_on_violation=False)
+    assert (a["distinct"], a["generated"], a["depth"]) == (189, 371, 7)
+    m = lower_model("MiniWindow", [SPECS], cfg)
+    assert not m.warnings and m.state_bits == 11
+    for items in (False, True):
+        r = run_host(m, dump=True, max_states=100000, items=items)
+        assert (r["distinct"], r["generated"], r["depth"], r["levels"], r["fail"]) == (
+            a["distinct"], a["generated"], a["depth"], a["levels"], 0)
+        assert r["first_violated"] is None
+        assert state_digest([m.state_text(row) for row in r["states"]]) == state_digest(a["states"])
+    assert StateDecoder(m.meta()).texts(np.array(r["states"], dtype=np.uint64)) == [m.state_text(row) for row in r["states"]]

@@ -13,7 +13,7 @@ def checker(name, **kw):
     return Checker(name, **kw)
 
 
-@pytest.mark.parametrize("name", ["miniqueue", "minimsgs"])
+@pytest.mark.parametrize("name", ["miniqueue", "minimsgs", "miniwindow"])
 def test_zz_sequence_models_match_oracle_a(name, goldens):
     """Sequences / tuples / RECURSIVE / \\X: counts, widths and the decoded state set against Oracle A."""
     from golden.make_golden import state_digest
