@@ -57,7 +57,7 @@ _TOKEN_RE = re.compile(
   | (?P<str>"(?:[^"\\]|\\.)*")
   | (?P<id>[A-Za-z_][A-Za-z0-9_]*)
   | (?P<bsword>\\[A-Za-z]+)
-  | (?P<op>/\\|\\/|\|->|<=>|->|<-|==|=>|=<|<=|>=|/=|\.\.|<<|>>|\[\]|<>|::|[=<>+\-*/()\[\]{},:.!@'~\#\\^|&])
+  | (?P<op>/\\|\\/|\|->|<=>|->|<-|==|=>|=<|<=|>=|/=|\.\.|<<|>>|\[\]|<>|::|[=<>+\-*/()\[\]{},:.!@'~\#\\^|&%])
     """,
     re.VERBOSE,
 )

@@ -73,7 +73,7 @@ _BINOPS = {
     "\\in": (5, "N"), "\\notin": (5, "N"), "\\subseteq": (5, "N"),
     "\\union": (8, "L"), "\\intersect": (8, "L"), "\\": (8, "L"),
     "..": (9, "N"),
-    "+": (10, "L"), "-": (11, "L"),
+    "+": (10, "L"), "-": (11, "L"), "%": (11, "L"),
     "\\X": (12, "L"),                      # n-ary: A \X B \X C is the set of triples
     "*": (13, "L"), "\\div": (13, "L"), "\\o": (13, "L"),
 }

@@ -1146,6 +1146,25 @@ class Lowerer:
                 return self.mk_int(f"({A.s} - {B.s})", A.lo - B.hi, A.hi - B.lo)
             c = [A.lo * B.lo, A.lo * B.hi, A.hi * B.lo, A.hi * B.hi]
             return self.mk_int(f"({A.s} * {B.s})", min(c), max(c))
+        if op in ("\\div", "%"):
+            # Integers: floor division and the modulus with a positive divisor (TLA+ defines a % b only for b > 0)
+            if isinstance(a, SUnion):
+                a = self.narrow_union(a, "int")
+            if isinstance(b, SUnion):
+                b = self.narrow_union(b, "int")
+            if is_int_const(a) and is_int_const(b):
+                if b <= 0:
+                    raise LowerError(f"{op} with the non-positive divisor {b}")
+                return a // b if op == "\\div" else a % b
+            A, B = self.as_sint(a), self.as_sint(b)
+            if B.lo <= 0:
+                raise LowerError(f"{op}: the divisor may be non-positive ({B.lo}..{B.hi})")
+            if op == "\\div":
+                c = [A.lo // B.lo, A.lo // B.hi, A.hi // B.lo, A.hi // B.hi]
+                e = f"({A.s} / {B.s})" if A.lo >= 0 else f"(({A.s}) >= 0 ? ({A.s}) / ({B.s}) : -((-({A.s}) + ({B.s}) - 1) / ({B.s})))"
+                return self.mk_int(e, min(c), max(c))
+            e = f"({A.s} % {B.s})" if A.lo >= 0 else f"(((({A.s}) % ({B.s})) + ({B.s})) % ({B.s}))"
+            return self.mk_int(e, 0, min(B.hi - 1, A.hi) if A.lo >= 0 else B.hi - 1)
         if op == "..":
             return self.interval(a, b)
         if op == "\\o":

@@ -596,7 +596,7 @@ class Interp:
             return tla_eq(a, b)
         if op == "#":
             return not tla_eq(a, b)
-        if op in ("<", ">", "<=", ">=", "+", "-", "*", "\\div", ".."):
+        if op in ("<", ">", "<=", ">=", "+", "-", "*", "\\div", "%", ".."):
             for x in (a, b):
                 if isinstance(x, bool) or not isinstance(x, int):
                     raise EvalError(f"operator {op} applied to non-integer {fmt(x)}")
@@ -614,8 +614,10 @@ class Interp:
                 return a - b
             if op == "*":
                 return a * b
-            if op == "\\div":
-                return a // b
+            if op in ("\\div", "%"):
+                if b <= 0:
+                    raise EvalError(f"{op} with the non-positive divisor {b}")
+                return a // b if op == "\\div" else a % b
             return frozenset(range(a, b + 1))
         if op == "\\o":
             if not isinstance(a, tuple) or not isinstance(b, tuple):

@@ -159,3 +159,34 @@ def test_miniwindow_runtime_bounds_and_products():
         assert r["first_violated"] is None
         assert state_digest([m.state_text(row) for row in r["states"]]) == state_digest(a["states"])
     assert StateDecoder(m.meta()).texts(np.array(r["states"], dtype=np.uint64)) == [m.state_text(row) for row in r["states"]]
+
+
+def test_integer_division_and_modulus(tmp_path):
+    """Integers: \\div (floor) and % with constant and run-time operands, negative dividends included."""
+    import tla_interp
+    (tmp_path / "DivMod.tla").write_text("""---- MODULE DivMod ----
+EXTENDS Integers
+VARIABLES x, y, d
+TypeOk == x \\in -7 .. 7 /\\ y \\in 0 .. 6 /\\ d \\in 1 .. 3
+Init == x = -7 /\\ y = 0 /\\ d = 1
+Step == /\\ x < 7
+        /\\ x' = x + 1
+        /\\ y' = (x + 7) % 5 + (x \\div 4 + 2) % 2
+        /\\ d' = (d % 3) + 1
+Wrap == /\\ x = 7
+        /\\ x' = (x \\div d) - 7
+        /\\ y' = x % d
+        /\\ UNCHANGED d
+Next == Step \\/ Wrap
+Sane == y = y % 7 /\\ (x \\div d) * d + x % d = x
+====
+""")
+    cfg = "INIT Init\nNEXT Next\nINVARIANTS TypeOk Sane\nCHECK_DEADLOCK FALSE\n"
+    a = tla_interp.run_bfs("DivMod", [str(tmp_path)], cfg, collect_states=True, stop_on_violation=False)
+    assert all(v is None for v in a["first_violation_level"].values()) and a["distinct"] >= 15
+    m = lower_model("DivMod", [str(tmp_path)], cfg)
+    r = run_host(m, dump=True, max_states=10000)
+    assert (r["distinct"], r["generated"], r["depth"], r["levels"], r["fail"]) == (
+        a["distinct"], a["generated"], a["depth"], a["levels"], 0)
+    assert r["first_violated"] is None
+    assert state_digest([m.state_text(row) for row in r["states"]]) == state_digest(a["states"])
