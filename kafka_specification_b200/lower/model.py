@@ -68,6 +68,7 @@ class TypeInference:
     def __init__(self, lw: Lowerer):
         self.lw = lw
         self.found: dict[str, list] = {}     # var -> [(steps, Ty)]
+        self.seq_caps: dict[str, int] = {}   # var -> bound from a conjunct `Len(var) <= e` / `Len(var) < e` of the layout operator
 
     def type_from_setval(self, v) -> L.Ty:
         lw = self.lw
@@ -213,6 +214,19 @@ class TypeInference:
                 target, defctx, args = op
                 body, c2, fm2, env2 = lw.bind_call(target, defctx, args, ctx, fm, env)
                 self.collect(body, c2, fm2, env2)
+            return
+        if k == "binop" and e[1] in ("<=", "<") and e[2][0] == "app" and e[2][1] == "Len" and len(e[2][2]) == 1:
+            # `Len(v) <= N` next to `v \in Seq(S)` in the type invariant bounds the sequence's layout (a checked bound,
+            # like an explicit `\* kspec: CAPACITY v = N`, which takes precedence)
+            p = self.as_path(e[2][2][0], ctx, fm, env)
+            if p is not None and not p[1]:
+                try:
+                    bound = lw.ev(e[3], ctx, fm, env, None)
+                except LowerError:
+                    return
+                if is_int_const(bound):
+                    cap = bound if e[1] == "<=" else bound - 1
+                    self.seq_caps[p[0]] = min(cap, self.seq_caps.get(p[0], cap))
             return
         if k == "binop" and e[1] in ("\\in", "\\subseteq"):
             p = self.as_path(e[2], ctx, fm, env)
@@ -566,6 +580,10 @@ def lower_model(module: str, search_dirs: list[str], cfg_text: str, name: str | 
                 ty.set_cap(cap)
             else:
                 ty = L.TSet(ty.elem, cap)
+        if isinstance(ty, L.TSeq) and ty.cap is None and v in ti.seq_caps:
+            if ti.seq_caps[v] < 0:
+                raise LowerError(f"Len({v}) is bounded by a negative number in {layout_op}")
+            ty.set_cap(ti.seq_caps[v])
         if v in cfg.prefix:
             apply_prefix(ty, *cfg.prefix[v])
         lay.var_types[v] = ty

@@ -109,9 +109,14 @@ def test_miniqueue_violation_and_capacity_trap():
     m = lower_model("MiniQueue", [tmp], cfg)
     r = run_host(m)
     assert r["first_violated"] == "NeverFull" and r["first_violated_level"] == lvl
-    # a sequence variable without a bound is rejected with the hint to give one ...
+    # the bound of a sequence comes from `\* kspec: CAPACITY`, else from a conjunct `Len(v) <= N` of the type invariant
+    # (MiniQueue's TypeOk has one) ...
+    plain = open(os.path.join(SPECS, "MiniQueue.cfg")).read()
+    m1 = lower_model("MiniQueue", [SPECS], plain.replace("\\* kspec: CAPACITY queue = Cap", ""))
+    assert m1.layout["types"]["queue"]["cap"] == 3 and m1.layout == lower_model("MiniQueue", [SPECS], plain).layout
+    # ... and a sequence variable with neither is rejected with the hint to give one (MiniMsgs' TypeOk has no Len bound)
     try:
-        lower_model("MiniQueue", [SPECS], cfg.replace("\\* kspec: CAPACITY queue = Cap", "").replace("NeverFull", "SumOk"))
+        lower_model("MiniMsgs", [SPECS], open(os.path.join(SPECS, "MiniMsgs.cfg")).read().replace("\\* kspec: CAPACITY inbox = MaxLen", ""))
         assert False, "expected a LowerError"
     except LowerError as e:
         assert "CAPACITY" in str(e)
