@@ -28,6 +28,10 @@ def pytest_collection_modifyitems(config, items):
     late = [it for it in items if it.name.startswith(RUN_LAST) or it.fspath.basename.startswith("test_zz_")]
     if late:
         ids = {id(it) for it in late}
+        # among the late ones: first those whose expected results are fully established on the CPU (test_zz_*: models
+        # that agree with the oracles state for state on the host), last the features that only a GPU can exercise
+        # at all (spill ring, checkpoint / recover)
+        late.sort(key=lambda it: 0 if it.fspath.basename.startswith("test_zz_") else 1)
         items[:] = [it for it in items if id(it) not in ids] + late
 
 
